@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py - audio samples/sec of the Harmonic(100)+FilteredNoise(65) decoder.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+      --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], per GPU): batch 32 x 64000 samples @16 kHz,
+F=1000 frames, K=100 harmonics, 65 noise bands - the `ae.gin` DAG
+Harmonic -> FilteredNoise -> Add, from raw network outputs (get_controls
+included), through ddsp_b200.ProcessorGroup.  One "step" = one decoder forward
+over one batch.  Weak scaling: every GPU runs the same per-GPU batch on its own
+shard, no data-path collective.
+
+One JSON line on stdout (rank 0).  See the task contract for the keys.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES = 64000
+N_FRAMES = 1000
+N_HARM = 100
+N_BANDS = 65
+SAMPLE_RATE = 16000
+BATCH_PER_GPU = 32
+L2_BYTES = 126 * 1024 * 1024
+
+# Algorithmic bytes per batch item (BASELINE.md section 3 / SURVEY.md 8d), fp32.
+BYTES_HARMONIC = 4 * (2 * N_FRAMES + N_FRAMES * N_HARM) + 4 * N_SAMPLES  # 664000
+BYTES_NOISE = 4 * N_FRAMES * N_BANDS + 4 * N_SAMPLES                     # 516000
+BYTES_DECODER_FUSED = (4 * (2 * N_FRAMES + N_FRAMES * N_HARM + N_FRAMES * N_BANDS)
+                       + 4 * N_SAMPLES)                                  # 924000
+
+
+def _measured_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as f:
+      return float(json.load(f)['hbm_gbs']), 'measured'
+  return 6650.0, 'fallback'
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+  QUERY = ('clocks.sm,clocks.max.sm,power.draw,'
+           'clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,'
+           'clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index = index
+    self.rows = []
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+           '--format=csv,noheader,nounits', '-lms', '50'],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi absent']}
+    time.sleep(0.06)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, smax, reasons = [], None, set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    for row in self.rows:
+      parts = [p.strip() for p in row.split(',')]
+      if len(parts) < 7:
+        continue
+      try:
+        sm.append(float(parts[0]))
+        smax = float(parts[1])
+      except ValueError:
+        continue
+      for name, val in zip(names, parts[3:7]):
+        if val.lower().startswith('active'):
+          reasons.add(name)
+    return {'sm_mhz': statistics.median(sm) if sm else None,
+            'sm_max_mhz': smax, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_host_inputs(batch, seed):
+  from tests.util import synth_inputs
+  inp = synth_inputs(batch, N_FRAMES, N_HARM, N_BANDS, N_SAMPLES, seed=seed)
+  return {k: inp[k] for k in ['amps', 'harmonic_distribution', 'f0_hz',
+                              'noise_magnitudes']}
+
+
+# ----------------------------------------------------------------------------
+# reference arm: the CPU port of the reference decoder, host cores only
+# ----------------------------------------------------------------------------
+def cpu_reference_throughput(items, repeats=1, threads=None):
+  """samples/s of oracle/ref_port_torch.decoder on `items` batch items."""
+  import torch
+  from oracle import ref_port_torch as rp
+  if threads:
+    torch.set_num_threads(threads)
+  inp = make_host_inputs(items, seed=99)
+  t = {k: torch.from_numpy(v) for k, v in inp.items()}
+  best = None
+  for _ in range(repeats):
+    t0 = time.perf_counter()
+    rp.decoder(t['amps'], t['harmonic_distribution'], t['f0_hz'],
+               t['noise_magnitudes'], n_samples=N_SAMPLES,
+               sample_rate=SAMPLE_RATE, window_size=0)
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+  return items * N_SAMPLES / best, best, torch.get_num_threads()
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return  # other ranks exit 0 without work
+  import torch
+  cores = torch.get_num_threads()
+  items = 8  # bounded sample of the B=32 workload: 8 items per step
+  rates, times = [], []
+  for i in range(args.warmup + args.steps):
+    rate, dt, cores = cpu_reference_throughput(items)
+    if i >= args.warmup:
+      rates.append(rate)
+      times.append(dt)
+  value = items * N_SAMPLES * len(times) / sum(times)
+  line = {
+      'impl': 'reference', 'metric': 'audio samples/sec (Harmonic+FilteredNoise decoder)',
+      'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus,
+      'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': 1e3 * sum(times) / len(times), 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': 'ae.gin decoder Harmonic(100)+FilteredNoise(65)+Add, '
+                             'N=64000 @16kHz, F=1000 (configs[1] shapes)',
+                 'batch_per_step': items},
+      'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores,
+                       'kind': 'port',
+                       'sample': '%d of the 32 batch items per step (torch-CPU '
+                                 'op-by-op float32 port of ddsp core/synths; '
+                                 'TensorFlow is not installable here)' % items},
+      'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  import ddsp_b200
+  from ddsp_b200 import _lib, core
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py (ours) needs a CUDA device; there is no CPU path.')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=dev)
+  lib = _lib.load()
+  B = args.batch
+
+  harm = ddsp_b200.Harmonic(n_samples=N_SAMPLES, sample_rate=SAMPLE_RATE)
+  noise = ddsp_b200.FilteredNoise(n_samples=N_SAMPLES, window_size=0, seed=rank)
+  add = ddsp_b200.Add()
+  group = ddsp_b200.ProcessorGroup(dag=[
+      (harm, ['amps', 'harmonic_distribution', 'f0_hz']),
+      (noise, ['noise_magnitudes']),
+      (add, ['filtered_noise/signal', 'harmonic/signal'])])
+
+  # A ring of distinct input sets larger than 2x L2 so every step reads HBM.
+  host = make_host_inputs(B, seed=1234 + rank)
+  set_bytes = sum(v.nbytes for v in host.values()) + 4 * B * N_SAMPLES
+  n_sets = max(2, -(-2 * L2_BYTES // set_bytes))
+  dev_sets = []
+  for s in range(n_sets):
+    d = {k: torch.from_numpy(v).to(dev) for k, v in host.items()}
+    if s:
+      d['amps'] = d['amps'] + 0.01 * s   # distinct contents, same statistics
+    dev_sets.append(d)
+  pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+  h2d_bytes = sum(v.numel() * 4 for v in pinned.values())
+  out_host = torch.empty((B, N_SAMPLES), dtype=torch.float32).pin_memory()
+  d2h_bytes = out_host.numel() * 4
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  def timed(fn, steps, warmup):
+    for i in range(warmup):
+      fn(i)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+      fn(warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      tms = torch.tensor([ms], device=dev)
+      dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+      ms = float(tms.item())
+    return ms
+
+  # -- value: whole decoder step, inputs resident in HBM ----------------------
+  def step_resident(i):
+    group(dev_sets[i % n_sets])
+
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  c0 = lib.ddsp_b200_launch_count()
+  ms_total = timed(step_resident, args.steps, args.warmup)
+  launches = lib.ddsp_b200_launch_count() - c0
+  launches_timed = launches * args.steps // (args.steps + args.warmup)
+  clocks = sampler.stop() if rank == 0 else None
+  ms_per_step = ms_total / args.steps
+  value = world * B * N_SAMPLES / (ms_per_step * 1e-3)
+
+  # -- e2e: host buffers in, host audio out, copies inside the timed region ---
+  def step_e2e(i):
+    feats = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+    audio = group(feats)
+    out_host.copy_(audio, non_blocking=True)
+    torch.cuda.current_stream().synchronize()   # the caller reads the result
+
+  ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2)) / args.steps
+  e2e_value = world * B * N_SAMPLES / (ms_e2e * 1e-3)
+
+  # -- per-kernel durations for the roofline (rank 0 reports) -----------------
+  ctl = []
+  for d in dev_sets:
+    hc = harm.get_controls(d['amps'], d['harmonic_distribution'], d['f0_hz'])
+    nc = noise.get_controls(d['noise_magnitudes'])
+    ctl.append((hc, nc))
+  audio_bufs = [torch.empty((B, N_SAMPLES), dtype=torch.float32, device=dev)
+                for _ in range(n_sets)]
+
+  def harm_only(i):
+    harm.get_signal(out=audio_bufs[i % n_sets], **ctl[i % n_sets][0])
+
+  def noise_only(i):
+    noise.get_signal(out=audio_bufs[i % n_sets], accumulate=True,
+                     **ctl[i % n_sets][1])
+
+  def controls_only(i):
+    d = dev_sets[i % n_sets]
+    harm.get_controls(d['amps'], d['harmonic_distribution'], d['f0_hz'])
+    noise.get_controls(d['noise_magnitudes'])
+
+  k_steps = max(args.steps, 20)
+  ms_harm = timed(harm_only, k_steps, 5) / k_steps
+  ms_noise = timed(noise_only, k_steps, 5) / k_steps
+  ms_ctl = timed(controls_only, k_steps, 5) / k_steps
+
+  # -- secondary workload: C3 (B=256) for context ------------------------------
+  extra = {}
+  if args.extra and rank == 0:
+    try:
+      B3 = 256
+      h3 = make_host_inputs(B3, seed=77)
+      d3 = {k: torch.from_numpy(v).to(dev) for k, v in h3.items()}
+      ms3 = timed(lambda i: group(d3), 10, 3) / 10
+      extra['c3_batch256_samples_per_s'] = B3 * N_SAMPLES / (ms3 * 1e-3)
+      extra['c3_ms_per_step'] = ms3
+      del d3
+    except Exception as e:  # pylint: disable=broad-except
+      extra['c3_error'] = repr(e)
+
+  if rank != 0:
+    if world > 1:
+      dist.barrier()
+      dist.destroy_process_group()
+    return
+
+  peak, peak_src = _measured_peaks()
+  dom_is_harm = ms_harm >= ms_noise
+  dom_ms = ms_harm if dom_is_harm else ms_noise
+  dom_bytes = (BYTES_HARMONIC if dom_is_harm else BYTES_NOISE + 4 * N_SAMPLES) * B
+  achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+  roofline = {
+      'bound': 'hbm', 'kernel': 'harmonic_forward' if dom_is_harm else
+               'filtered_noise_forward(accumulate)',
+      'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+      'frac': achieved / peak, 'peak_source': peak_src + ' (MEASURED_PEAKS.json hbm_gbs)',
+      'traffic': None,
+      'algorithmic_bytes_per_launch': dom_bytes,
+      'kernel_ms': {'harmonic_forward': ms_harm,
+                    'filtered_noise_forward': ms_noise,
+                    'controls(2 kernels)': ms_ctl},
+      'decoder_fused_frac': (BYTES_DECODER_FUSED * B / (ms_per_step * 1e-3) / 1e9) / peak,
+  }
+
+  # -- cpu baseline: bounded sample of the same workload on the host cores ----
+  cpu = None
+  if not args.no_cpu_baseline:
+    items = 8
+    rate, dt, cores = cpu_reference_throughput(items, repeats=2)
+    cpu = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+           'sample': '%d of the %d batch items (torch-CPU op-by-op float32 port '
+                     'of ddsp core/synths, %.2f s)' % (items, B, dt)}
+
+  line = {
+      'metric': 'audio samples/sec (Harmonic+FilteredNoise decoder)',
+      'value': value, 'unit': 'samples/s', 'n_gpus': world,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'f32', 'data': 'synthetic',
+      'config': {
+          'workload': 'configs[1]: ae.gin decoder Harmonic(100)+FilteredNoise(65)'
+                      '+Add via ProcessorGroup (get_controls + get_signal), '
+                      'batch %d per GPU, N=64000 @16kHz, F=1000' % B,
+          'batch_per_gpu': B, 'global_batch': B * world,
+          'l2_policy': 'ring of %d distinct input/output sets (%.0f MB > 2x L2)'
+                       % (n_sets, n_sets * set_bytes / 1e6),
+          'noise': 'in-kernel Philox4x32-10', 'parallelism': 'batch-sharded replicas, no collective',
+      },
+      'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e,
+              'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},
+      'gpu_launches': int(launches_timed),
+      'clocks': clocks,
+      'roofline': roofline,
+      'cpu_baseline': cpu,
+  }
+  line.update(extra)
+  print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=50)
+  ap.add_argument('--warmup', type=int, default=10)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--batch', type=int, default=BATCH_PER_GPU,
+                  help='batch items per GPU (configs[1] = 32)')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--extra', type=int, default=1,
+                  help='also time the B=256 (configs[2]) step on rank 0')
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3)
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -1,0 +1,380 @@
+"""Host-side mirror of the hot-path functions of `ddsp/core.py`.
+
+Same names, argument meaning and error behaviour as the reference (file:line
+cited per function); the arithmetic happens in libddsp_b200.so (hand-written
+sm_100a kernels) through the ctypes C ABI in `_lib.py`.  torch is plumbing:
+device memory and streams.  There is no CPU fallback.
+"""
+from collections import abc
+from typing import Any, Dict, Optional, Sequence, Text
+
+import numpy as np
+import torch
+
+from ddsp_b200 import _lib
+
+AMP_METHODS = {'window': _lib.AMP_WINDOW, 'linear': _lib.AMP_LINEAR}
+
+
+# ----------------------------------------------------------------------------
+# Utility functions (core.py:30-129)
+# ----------------------------------------------------------------------------
+def _device():
+  if not torch.cuda.is_available():
+    raise RuntimeError(
+        'ddsp_b200 needs a CUDA device (B200, sm_100a); there is no CPU '
+        'fallback.')
+  return torch.device('cuda', torch.cuda.current_device())
+
+
+def torch_float32(x, device=None):
+  """`tf_float32` (core.py:31-36): a contiguous float32 CUDA tensor."""
+  if isinstance(x, torch.Tensor):
+    if x.is_cuda and device is None:
+      return x.to(torch.float32).contiguous()
+    return x.to(device=device or _device(), dtype=torch.float32).contiguous()
+  return torch.as_tensor(np.asarray(x, dtype=np.float32),
+                         device=device or _device()).contiguous()
+
+
+tf_float32 = torch_float32  # the reference's name for the same coercion
+
+
+def make_iterable(x):
+  """core.py:39-47."""
+  if x is None:
+    return []
+  elif isinstance(x, (np.ndarray, torch.Tensor)):
+    return [x]
+  else:
+    return x if isinstance(x, abc.Iterable) else [x]
+
+
+def to_dict(x, keys):
+  """core.py:50-61."""
+  if isinstance(x, dict):
+    return x
+  else:
+    x = make_iterable(x)
+    if len(keys) != len(x):
+      raise ValueError(f'Keys: {keys} must be the same length as {x}')
+    return dict(zip(keys, x))
+
+
+def nested_keys(nested_dict: Dict[Text, Any], delimiter: Text = '/',
+                prefix: Text = '') -> Sequence[Text]:
+  """core.py:78-102."""
+  keys = []
+  for k, v in nested_dict.items():
+    key = k if not prefix else f'{prefix}{delimiter}{k}'
+    if not isinstance(v, dict):
+      keys.append(key)
+    else:
+      keys += nested_keys(v, prefix=key)
+  return keys
+
+
+def nested_lookup(nested_key: Text, nested_dict: Dict[Text, Any],
+                  delimiter: Text = '/'):
+  """core.py:105-129."""
+  keys = nested_key.split(delimiter)
+  value = nested_dict
+  for key in keys:
+    try:
+      value = value[key]
+    except KeyError:
+      raise KeyError(f'Key \'{key}\' as a part of nested key \'{nested_key}\' '
+                     'not found during nested dictionary lookup, out of '
+                     f'available keys: {nested_keys(nested_dict)}')
+  return value
+
+
+def _stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+  return 0 if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------
+# Scaling (core.py:386-404) - used by callers that want the bare function; the
+# processors call the fused controls kernels instead.
+# ----------------------------------------------------------------------------
+def exp_sigmoid(x, exponent=10.0, max_value=2.0, threshold=1e-7):
+  """core.py:386-404.  Default arguments run the CUDA controls kernel."""
+  x = torch_float32(x)
+  if (exponent, max_value, threshold) == (10.0, 2.0, 1e-7):
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().ddsp_b200_noise_controls(
+        _ptr(x), _ptr(out), x.numel(), 0.0, 1, _stream()))
+    return out
+  return max_value * torch.sigmoid(x)**float(np.log(exponent)) + threshold
+
+
+# ----------------------------------------------------------------------------
+# Harmonic synthesis (core.py:1048-1111)
+# ----------------------------------------------------------------------------
+def harmonic_controls(amplitudes, harmonic_distribution, f0_hz, sample_rate,
+                      scale=True, normalize_below_nyquist=True):
+  """synths.Harmonic.get_controls arithmetic (synths.py:94-121): exp_sigmoid,
+  core.normalize_harmonics (core.py:894-907)."""
+  amplitudes = torch_float32(amplitudes)
+  hd = torch_float32(harmonic_distribution)
+  f0_hz = torch_float32(f0_hz)
+  if hd.dim() != 3 or amplitudes.dim() != 3 or f0_hz.dim() != 3:
+    raise ValueError('Harmonic controls must be 3-D [batch, frames, channels]; '
+                     f'got {tuple(amplitudes.shape)}, {tuple(hd.shape)}, '
+                     f'{tuple(f0_hz.shape)}.')
+  b, f, k = hd.shape
+  if tuple(amplitudes.shape) != (b, f, 1) or tuple(f0_hz.shape) != (b, f, 1):
+    raise ValueError(
+        f'amplitudes {tuple(amplitudes.shape)} and f0_hz {tuple(f0_hz.shape)} '
+        f'must be [{b}, {f}, 1] to match harmonic_distribution.')
+  amps_out = torch.empty_like(amplitudes)
+  hd_out = torch.empty_like(hd)
+  flags = ((_lib.CTL_SCALE if scale else 0) |
+           (_lib.CTL_NYQUIST if normalize_below_nyquist else 0))
+  _lib.check(_lib.load().ddsp_b200_harmonic_controls(
+      _ptr(amplitudes), _ptr(hd), _ptr(f0_hz), _ptr(amps_out), _ptr(hd_out),
+      b, f, k, float(sample_rate), flags, _stream()))
+  return amps_out, hd_out
+
+
+def harmonic_synthesis(frequencies,
+                       amplitudes,
+                       harmonic_shifts=None,
+                       harmonic_distribution=None,
+                       n_samples: int = 64000,
+                       sample_rate: int = 16000,
+                       amp_resample_method: Text = 'window',
+                       use_angular_cumsum: bool = False,
+                       out: Optional[torch.Tensor] = None,
+                       accumulate: bool = False,
+                       phase_mode: Text = 'recurrence'):
+  """core.harmonic_synthesis (core.py:1048-1111) as one fused kernel.
+
+  `use_angular_cumsum` is accepted for API parity; phase is always accumulated
+  wrapped and exactly (64-bit fixed point), which is what angular_cumsum
+  approximates (core.py:803-817) - see DESIGN.md "phase".
+  """
+  del use_angular_cumsum
+  if harmonic_shifts is not None:
+    raise NotImplementedError(
+        'harmonic_shifts is outside the Harmonic processor path '
+        '(synths.py:138-146 never passes it).')
+  frequencies = torch_float32(frequencies)
+  amplitudes = torch_float32(amplitudes)
+  if harmonic_distribution is not None:
+    harmonic_distribution = torch_float32(harmonic_distribution)
+  if amp_resample_method not in ('nearest', 'linear', 'cubic', 'window'):
+    # core.py:632-634
+    raise ValueError('Method ({}) is invalid. Must be one of {}.'.format(
+        amp_resample_method, "['nearest', 'linear', 'cubic', 'window']"))
+  if amp_resample_method not in AMP_METHODS:
+    raise NotImplementedError(
+        f"amp_resample_method='{amp_resample_method}' is not built; "
+        "'window' and 'linear' are.")
+  if frequencies.dim() != 3 or amplitudes.dim() != 3:
+    # core.py:670-672 (the window upsampler only takes 3-D inputs)
+    raise ValueError('Upsample_with_windows() only supports 3 dimensions, '
+                     'not {}.'.format(list(amplitudes.shape)))
+  b, f, _ = frequencies.shape
+  k = 1 if harmonic_distribution is None else int(harmonic_distribution.shape[-1])
+  n_samples = int(n_samples)
+  if amp_resample_method == 'window':
+    if f >= n_samples:
+      # core.py:682-685
+      raise ValueError('Upsample with windows cannot be used for downsampling'
+                       'More input frames ({}) than output timesteps ({})'.format(
+                           f + 1, n_samples))
+    if n_samples % f != 0:
+      # core.py:687-693
+      raise ValueError(
+          'For upsampling, the target the number of timesteps must be divisible '
+          'by the number of input frames{}. (timesteps:{}, frames:{}, '
+          'add_endpoint={}).'.format('', n_samples, f + 1, True))
+  if out is None:
+    out = torch.empty((b, n_samples), dtype=torch.float32,
+                      device=frequencies.device)
+    accumulate = False
+  mode = {'recurrence': _lib.PHASE_RECURRENCE, 'direct': _lib.PHASE_DIRECT}[
+      phase_mode]
+  _lib.check(_lib.load().ddsp_b200_harmonic_forward(
+      _ptr(frequencies), _ptr(amplitudes), _ptr(harmonic_distribution),
+      _ptr(out), b, f, k, n_samples, float(sample_rate),
+      AMP_METHODS[amp_resample_method], mode, int(bool(accumulate)), _stream()))
+  return out
+
+
+# ----------------------------------------------------------------------------
+# Time-varying FIR / filtered noise (core.py:1316-1655)
+# ----------------------------------------------------------------------------
+def get_fft_size(frame_size: int, ir_size: int, power_of_2: bool = True) -> int:
+  """core.py:1317-1335 (kept for API parity; the CUDA path is time-domain)."""
+  convolved_frame_size = ir_size + frame_size - 1
+  if power_of_2:
+    return int(2**np.ceil(np.log2(convolved_frame_size)))
+  raise NotImplementedError('power_of_2=False needs scipy.fftpack.')
+
+
+def frequency_impulse_response(magnitudes, window_size: int = 0):
+  """core.frequency_impulse_response (core.py:1534-1565)."""
+  magnitudes = torch_float32(magnitudes)
+  nb = int(magnitudes.shape[-1])
+  lib = _lib.load()
+  s = lib.ddsp_b200_ir_size(nb, int(window_size))
+  if s < 0:
+    raise ValueError(f'frequency_impulse_response needs >= 2 frequencies, got {nb}.')
+  ir = torch.empty(tuple(magnitudes.shape[:-1]) + (s,), dtype=torch.float32,
+                   device=magnitudes.device)
+  bf = magnitudes.numel() // nb
+  _lib.check(lib.ddsp_b200_frequency_impulse_response(
+      _ptr(magnitudes), _ptr(ir), bf, nb, int(window_size), _stream()))
+  return ir
+
+
+def _crop_range(total_size, audio_size, ir_size, padding, delay_compensation):
+  """Index arithmetic of crop_and_compensate_delay (core.py:1338-1379),
+  including Python's slice semantics of `audio[:, start:-end]`."""
+  if padding == 'valid':
+    crop_size = ir_size + audio_size - 1
+  elif padding == 'same':
+    crop_size = audio_size
+  else:
+    raise ValueError('Padding must be \'valid\' or \'same\', instead '
+                     'of {}.'.format(padding))
+  crop = total_size - crop_size
+  start = ((ir_size - 1) // 2 - 1 if delay_compensation < 0
+           else delay_compensation)
+  end = crop - start
+  rng = range(total_size)[start:-end]
+  return start, len(rng), crop_size
+
+
+def fft_convolve(audio, impulse_response, padding: Text = 'same',
+                 delay_compensation: int = -1, out=None, accumulate=False):
+  """core.fft_convolve (core.py:1382-1473).
+
+  Computed as the mathematically identical direct-form time-varying FIR
+  (frame / rfft / multiply / irfft / overlap_and_add / crop folded into index
+  math) - the name is kept for drop-in compatibility.
+  """
+  audio = torch_float32(audio)
+  impulse_response = torch_float32(impulse_response)
+  batch_size, audio_size = audio.shape
+  if impulse_response.dim() == 2:
+    impulse_response = impulse_response[:, None, :]
+  ir_batch, n_ir_frames, ir_size = impulse_response.shape
+  if not (ir_batch == 1 and batch_size > 1) and batch_size != ir_batch:
+    # core.py:1441-1443
+    raise ValueError('Batch size of audio ({}) and impulse response ({}) must '
+                     'be the same.'.format(batch_size, ir_batch))
+  frame_size = int(np.ceil(audio_size / n_ir_frames))
+  n_audio_frames = -(-audio_size // frame_size)
+  if n_audio_frames != n_ir_frames:
+    # core.py:1452-1457
+    raise ValueError(
+        'Number of Audio frames ({}) and impulse response frames ({}) do not '
+        'match. For small hop size = ceil(audio_size / n_ir_frames), '
+        'number of impulse response frames must be a multiple of the audio '
+        'size.'.format(n_audio_frames, n_ir_frames))
+  fft_size = get_fft_size(frame_size, ir_size, power_of_2=True)
+  total_size = (n_ir_frames - 1) * frame_size + fft_size
+  start, out_len, crop_size = _crop_range(total_size, audio_size, ir_size,
+                                          padding, delay_compensation)
+  if out_len != crop_size:
+    # The reference's `audio[:, start:-end]` degenerates when end <= 0 (e.g.
+    # end == 0 yields an empty tensor).  Reproduce the empty case; refuse the
+    # rest rather than guess.
+    if out_len == 0:
+      return torch.empty((batch_size, 0), dtype=torch.float32,
+                         device=audio.device)
+    raise NotImplementedError(
+        'crop_and_compensate_delay slice is degenerate for this shape '
+        f'(start={start}, total={total_size}, crop={crop_size}).')
+  if out is None:
+    out = torch.empty((batch_size, crop_size), dtype=torch.float32,
+                      device=audio.device)
+    accumulate = False
+  _lib.check(_lib.load().ddsp_b200_fir_time_varying(
+      _ptr(audio), _ptr(impulse_response.contiguous()), _ptr(out), batch_size,
+      audio_size, n_ir_frames, ir_size, ir_batch,
+      _lib.PAD_SAME if padding == 'same' else _lib.PAD_VALID,
+      int(start), int(bool(accumulate)), _stream()))
+  return out
+
+
+def frequency_filter(audio, magnitudes, window_size: int = 0,
+                     padding: Text = 'same'):
+  """core.frequency_filter (core.py:1628-1655)."""
+  impulse_response = frequency_impulse_response(magnitudes,
+                                                window_size=window_size)
+  return fft_convolve(audio, impulse_response, padding=padding)
+
+
+def uniform_noise(batch_size, n_samples, seed=0, offset=0, device=None):
+  """Stand-in for tf.random.uniform([B, N], -1, 1) (synths.py:192-193):
+  Philox4x32-10 keyed by `seed`, counter (sample/4, batch, offset)."""
+  out = torch.empty((batch_size, n_samples), dtype=torch.float32,
+                    device=device or _device())
+  _lib.check(_lib.load().ddsp_b200_uniform_noise(
+      _ptr(out), batch_size, n_samples, int(seed) & (2**64 - 1),
+      int(offset) & (2**64 - 1), _stream()))
+  return out
+
+
+def filtered_noise(magnitudes, n_samples, window_size=257, noise=None, seed=0,
+                   offset=0, out=None, accumulate=False):
+  """FilteredNoise.get_signal arithmetic (synths.py:181-196): uniform noise ->
+  core.frequency_filter (core.py:1628-1655), fused where the shape allows."""
+  magnitudes = torch_float32(magnitudes)
+  if magnitudes.dim() != 3:
+    raise ValueError('magnitudes must be [batch, n_frames, n_filter_banks], got '
+                     f'{tuple(magnitudes.shape)}.')
+  b, f, nb = magnitudes.shape
+  n_samples = int(n_samples)
+  if noise is not None:
+    noise = torch_float32(noise)
+    if tuple(noise.shape) != (b, n_samples):
+      raise ValueError(f'noise must be [{b}, {n_samples}], got '
+                       f'{tuple(noise.shape)}.')
+  lib = _lib.load()
+  if out is None:
+    out = torch.empty((b, n_samples), dtype=torch.float32,
+                      device=magnitudes.device)
+    accumulate = False
+  ws_bytes = lib.ddsp_b200_filtered_noise_workspace(b, f, nb, n_samples,
+                                                    int(window_size))
+  workspace = (torch.empty((ws_bytes,), dtype=torch.uint8,
+                           device=magnitudes.device) if ws_bytes else None)
+  _lib.check(lib.ddsp_b200_filtered_noise_forward(
+      _ptr(magnitudes), _ptr(noise), int(seed) & (2**64 - 1),
+      int(offset) & (2**64 - 1), _ptr(out), b, f, nb, n_samples,
+      int(window_size), int(bool(accumulate)), _ptr(workspace), ws_bytes,
+      _stream()))
+  return out
+
+
+def noise_controls(magnitudes, initial_bias=-5.0, scale=True):
+  """FilteredNoise.get_controls arithmetic (synths.py:165-179)."""
+  magnitudes = torch_float32(magnitudes)
+  out = torch.empty_like(magnitudes)
+  _lib.check(_lib.load().ddsp_b200_noise_controls(
+      _ptr(magnitudes), _ptr(out), magnitudes.numel(), float(initial_bias),
+      int(bool(scale)), _stream()))
+  return out
+
+
+def add(signal_one, signal_two, out=None):
+  """processors.Add.get_signal (processors.py:174-176)."""
+  a = torch_float32(signal_one)
+  b = torch_float32(signal_two)
+  if a.shape != b.shape:
+    a, b = torch.broadcast_tensors(a, b)
+    a, b = a.contiguous(), b.contiguous()
+  if out is None:
+    out = torch.empty_like(a)
+  _lib.check(_lib.load().ddsp_b200_add(_ptr(a), _ptr(b), _ptr(out), a.numel(),
+                                       _stream()))
+  return out

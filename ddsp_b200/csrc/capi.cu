@@ -1,0 +1,325 @@
+// C ABI of libddsp_b200.so - argument validation + kernel launches.
+// See include/ddsp_b200.h for the contract and the reference file:line each
+// entry point replaces.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "controls.cuh"
+#include "harmonic.cuh"
+#include "harmonic_fast.cuh"
+#include "noise.cuh"
+#include "noise_fused.cuh"
+
+namespace ddsp {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+void count_launch() { ++g_launches; }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline int grid_for(int64_t n, int threads, int cap_per_sm = 8) {
+  int64_t blocks = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)kNumSMs * cap_per_sm;
+  return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+static constexpr size_t kMaxDynSmem = 200 * 1024;  // of 227 KB usable per CTA
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes, const char* name) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(
+        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_error("%s: cannot reserve %zu B of shared memory: %s", name, bytes,
+                cudaGetErrorString(e));
+      return DDSP_B200_E_CUDA;
+    }
+  }
+  return 0;
+}
+
+}  // namespace ddsp
+
+using namespace ddsp;
+
+extern "C" {
+
+int ddsp_b200_version(void) { return DDSP_B200_VERSION; }
+
+const char* ddsp_b200_last_error(void) { return g_err; }
+
+uint64_t ddsp_b200_launch_count(void) { return g_launches; }
+
+int ddsp_b200_harmonic_controls(const float* amps_in, const float* hd_in,
+                                const float* f0_hz, float* amps_out,
+                                float* hd_out, int B, int F, int K,
+                                float sample_rate, int flags, void* stream) {
+  DDSP_REQUIRE(amps_in && hd_in && f0_hz && amps_out && hd_out,
+               DDSP_B200_E_INVALID, "harmonic_controls: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 0 && K >= 1, DDSP_B200_E_INVALID,
+               "harmonic_controls: bad shape B=%d F=%d K=%d", B, F, K);
+  const int64_t rows = (int64_t)B * F;
+  if (rows == 0) return 0;
+  DDSP_REQUIRE(rows < (1ll << 31) / 32, DDSP_B200_E_INVALID,
+               "harmonic_controls: B*F too large");
+  const int threads = 256;
+  const int blocks = (int)((rows * 32 + threads - 1) / threads);
+  harmonic_controls_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      amps_in, hd_in, f0_hz, amps_out, hd_out, (int)rows, K,
+      sample_rate * 0.5f, flags);
+  DDSP_CHECK_LAUNCH("harmonic_controls");
+  return 0;
+}
+
+int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
+                               const float* hd, float* audio, int B, int F,
+                               int K, int N, float sample_rate, int amp_method,
+                               int phase_mode, int accumulate, void* stream) {
+  DDSP_REQUIRE(f0_hz && amps && audio, DDSP_B200_E_INVALID,
+               "harmonic_forward: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && K >= 1 && N >= 1, DDSP_B200_E_INVALID,
+               "harmonic_forward: bad shape B=%d F=%d K=%d N=%d", B, F, K, N);
+  DDSP_REQUIRE(hd != nullptr || K == 1, DDSP_B200_E_INVALID,
+               "harmonic_forward: harmonic_distribution is NULL but K=%d", K);
+  DDSP_REQUIRE(amp_method == DDSP_B200_AMP_WINDOW ||
+                   amp_method == DDSP_B200_AMP_LINEAR,
+               DDSP_B200_E_INVALID, "harmonic_forward: bad amp_method %d",
+               amp_method);
+  DDSP_REQUIRE(phase_mode == DDSP_B200_PHASE_RECURRENCE ||
+                   phase_mode == DDSP_B200_PHASE_DIRECT,
+               DDSP_B200_E_INVALID, "harmonic_forward: bad phase_mode %d",
+               phase_mode);
+  // upsample_with_windows raises unless N % F == 0 and F < N (core.py:682-693);
+  // the closed-form phase also needs an integer hop.
+  DDSP_REQUIRE(N % F == 0, DDSP_B200_E_INVALID,
+               "harmonic_forward: n_samples (%d) must be divisible by the "
+               "number of frames (%d)", N, F);
+  DDSP_REQUIRE(amp_method != DDSP_B200_AMP_WINDOW || F < N,
+               DDSP_B200_E_INVALID,
+               "harmonic_forward: window upsampling cannot downsample "
+               "(frames %d >= timesteps %d)", F, N);
+  DDSP_REQUIRE(sample_rate > 0.f, DDSP_B200_E_INVALID,
+               "harmonic_forward: sample_rate must be positive");
+  if (B == 0) return 0;
+  DDSP_REQUIRE(B <= 65535, DDSP_B200_E_INVALID,
+               "harmonic_forward: B=%d exceeds the 65535 grid limit", B);
+
+  HarmonicParams p;
+  p.f0 = f0_hz; p.amps = amps; p.hd = hd; p.audio = audio;
+  p.B = B; p.F = F; p.K = K; p.N = N; p.hop = N / F;
+  p.sample_rate = sample_rate;
+  p.nyquist = sample_rate * 0.5f;
+  p.inv_sr = 1.0 / (double)sample_rate;
+  p.amp_method = amp_method;
+  p.accumulate = accumulate;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_fast_supported(p)) {
+    int rc = launch_harmonic_fast(p, st);
+    if (rc != 1) return rc;   // 1 = declined, fall through to the generic path
+  }
+
+  p.Kp = (K + 3) & ~3;
+  // frames per tile: ~2048 samples, enough CTAs to fill the chip, bounded smem
+  int FT = std::max(1, 2048 / p.hop);
+  const int64_t want_ctas = 4ll * kNumSMs;
+  int ft_fill = (int)std::max<int64_t>(1, ((int64_t)B * F + want_ctas - 1) / want_ctas);
+  FT = std::min(FT, std::max(ft_fill, std::min(4, F)));
+  FT = std::min(FT, F);
+  while (FT > 1 && harm_smem_bytes(FT, p.Kp) > kMaxDynSmem) FT = (FT + 1) / 2;
+  DDSP_REQUIRE(harm_smem_bytes(FT, p.Kp) <= kMaxDynSmem, DDSP_B200_E_UNSUPPORTED,
+               "harmonic_forward: K=%d needs more shared memory than one CTA has",
+               K);
+  p.FT = FT;
+  const size_t smem = harm_smem_bytes(FT, p.Kp);
+  dim3 grid((F + FT - 1) / FT, B);
+  if (phase_mode == DDSP_B200_PHASE_DIRECT) {
+    int rc = set_smem(harmonic_generic_kernel<1>, smem, "harmonic_forward");
+    if (rc) return rc;
+    harmonic_generic_kernel<1><<<grid, kHarmThreads, smem, st>>>(p);
+  } else {
+    int rc = set_smem(harmonic_generic_kernel<0>, smem, "harmonic_forward");
+    if (rc) return rc;
+    harmonic_generic_kernel<0><<<grid, kHarmThreads, smem, st>>>(p);
+  }
+  DDSP_CHECK_LAUNCH("harmonic_forward");
+  return 0;
+}
+
+int ddsp_b200_noise_controls(const float* mag_in, float* mag_out, int64_t n,
+                             float initial_bias, int apply_scale, void* stream) {
+  DDSP_REQUIRE(mag_in && mag_out, DDSP_B200_E_INVALID,
+               "noise_controls: null pointer");
+  DDSP_REQUIRE(n >= 0, DDSP_B200_E_INVALID, "noise_controls: n < 0");
+  if (n == 0) return 0;
+  noise_controls_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      mag_in, mag_out, n, initial_bias, apply_scale);
+  DDSP_CHECK_LAUNCH("noise_controls");
+  return 0;
+}
+
+int ddsp_b200_ir_size(int nb, int window_size) {
+  if (nb < 2) return DDSP_B200_E_INVALID;
+  return make_ir_geom(nb, window_size).S;
+}
+
+int ddsp_b200_frequency_impulse_response(const float* mags, float* ir,
+                                         int64_t BF, int nb, int window_size,
+                                         void* stream) {
+  DDSP_REQUIRE(mags && ir, DDSP_B200_E_INVALID,
+               "frequency_impulse_response: null pointer");
+  DDSP_REQUIRE(nb >= 2 && BF >= 0, DDSP_B200_E_INVALID,
+               "frequency_impulse_response: need n_frequencies >= 2 (got %d)", nb);
+  if (BF == 0) return 0;
+  IrGeom g = make_ir_geom(nb, window_size);
+  const size_t smem = sizeof(float) * ((size_t)g.S0 + (size_t)kIrFrames * nb);
+  DDSP_REQUIRE(smem <= kMaxDynSmem, DDSP_B200_E_UNSUPPORTED,
+               "frequency_impulse_response: n_frequencies=%d too large", nb);
+  int rc = set_smem(ir_kernel, smem, "frequency_impulse_response");
+  if (rc) return rc;
+  const int64_t blocks = (BF + kIrFrames - 1) / kIrFrames;
+  DDSP_REQUIRE(blocks < (1ll << 31), DDSP_B200_E_INVALID,
+               "frequency_impulse_response: too many frames");
+  ir_kernel<<<(int)blocks, kIrThreads, smem, (cudaStream_t)stream>>>(mags, ir,
+                                                                     BF, g);
+  DDSP_CHECK_LAUNCH("frequency_impulse_response");
+  return 0;
+}
+
+int ddsp_b200_fir_time_varying(const float* audio, const float* ir, float* out,
+                               int B, int N, int F, int S, int ir_batch,
+                               int padding, int delay_compensation,
+                               int accumulate, void* stream) {
+  DDSP_REQUIRE(audio && ir && out, DDSP_B200_E_INVALID,
+               "fir_time_varying: null pointer");
+  DDSP_REQUIRE(B >= 0 && N >= 1 && F >= 1 && S >= 1, DDSP_B200_E_INVALID,
+               "fir_time_varying: bad shape B=%d N=%d F=%d S=%d", B, N, F, S);
+  // core.py:1441-1443
+  DDSP_REQUIRE(ir_batch == B || ir_batch == 1, DDSP_B200_E_INVALID,
+               "Batch size of audio (%d) and impulse response (%d) must be the "
+               "same.", B, ir_batch);
+  DDSP_REQUIRE(padding == DDSP_B200_PAD_SAME || padding == DDSP_B200_PAD_VALID,
+               DDSP_B200_E_INVALID,
+               "Padding must be 'valid' or 'same' (got code %d)", padding);
+  // core.py:1446-1457: frame = ceil(N / F); frame(pad_end) must yield F frames
+  const int frame = (N + F - 1) / F;
+  const int n_audio_frames = (N + frame - 1) / frame;
+  DDSP_REQUIRE(n_audio_frames == F, DDSP_B200_E_INVALID,
+               "Number of Audio frames (%d) and impulse response frames (%d) do "
+               "not match. For small hop size = ceil(audio_size / n_ir_frames), "
+               "number of impulse response frames must be a multiple of the "
+               "audio size.", n_audio_frames, F);
+  if (B == 0) return 0;
+  DDSP_REQUIRE(B <= 65535, DDSP_B200_E_INVALID,
+               "fir_time_varying: B=%d exceeds the 65535 grid limit", B);
+  // crop_and_compensate_delay (core.py:1338-1379)
+  const int out_len = (padding == DDSP_B200_PAD_VALID) ? (N + S - 1) : N;
+  const int start = delay_compensation < 0 ? ((S - 1) / 2 - 1)
+                                           : delay_compensation;
+  DDSP_REQUIRE(start >= 0, DDSP_B200_E_UNSUPPORTED,
+               "fir_time_varying: impulse response of %d taps gives a negative "
+               "automatic delay; pass delay_compensation >= 0", S);
+  const size_t smem = sizeof(float) * ((size_t)kFirThreads + S - 1);
+  DDSP_REQUIRE(smem <= kMaxDynSmem, DDSP_B200_E_UNSUPPORTED,
+               "fir_time_varying: impulse response of %d taps is beyond the "
+               "shared-memory FIR (long-IR convolution is not built yet)", S);
+  int rc = set_smem(fir_kernel, smem, "fir_time_varying");
+  if (rc) return rc;
+  dim3 grid((out_len + kFirThreads - 1) / kFirThreads, B);
+  fir_kernel<<<grid, kFirThreads, smem, (cudaStream_t)stream>>>(
+      audio, ir, out, N, F, S, frame, ir_batch == 1 ? 0 : F * S, start, out_len,
+      accumulate);
+  DDSP_CHECK_LAUNCH("fir_time_varying");
+  return 0;
+}
+
+int ddsp_b200_uniform_noise(float* out, int B, int N, uint64_t seed,
+                            uint64_t offset, void* stream) {
+  DDSP_REQUIRE(out, DDSP_B200_E_INVALID, "uniform_noise: null pointer");
+  DDSP_REQUIRE(B >= 0 && N >= 0, DDSP_B200_E_INVALID, "uniform_noise: bad shape");
+  if (B == 0 || N == 0) return 0;
+  const int64_t n = (int64_t)B * ((N + 3) / 4);
+  uniform_noise_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      out, B, N, seed, offset);
+  DDSP_CHECK_LAUNCH("uniform_noise");
+  return 0;
+}
+
+size_t ddsp_b200_filtered_noise_workspace(int B, int F, int nb, int N,
+                                          int window_size) {
+  if (nb < 2 || B <= 0 || F <= 0 || N <= 0) return 0;
+  if (noise_fused_supported(F, nb, N, window_size)) return 0;
+  IrGeom g = make_ir_geom(nb, window_size);
+  // generic path: IR [B,F,S] + noise [B,N]
+  return sizeof(float) * ((size_t)B * F * g.S + (size_t)B * N) + 256;
+}
+
+int ddsp_b200_filtered_noise_forward(const float* mags, const float* noise,
+                                     uint64_t seed, uint64_t offset,
+                                     float* audio, int B, int F, int nb, int N,
+                                     int window_size, int accumulate,
+                                     void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  DDSP_REQUIRE(mags && audio, DDSP_B200_E_INVALID,
+               "filtered_noise_forward: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && N >= 1, DDSP_B200_E_INVALID,
+               "filtered_noise_forward: bad shape B=%d F=%d N=%d", B, F, N);
+  DDSP_REQUIRE(nb >= 2, DDSP_B200_E_INVALID,
+               "filtered_noise_forward: need n_frequencies >= 2 (got %d)", nb);
+  const int frame = (N + F - 1) / F;
+  const int n_audio_frames = (N + frame - 1) / frame;
+  DDSP_REQUIRE(n_audio_frames == F, DDSP_B200_E_INVALID,
+               "Number of Audio frames (%d) and impulse response frames (%d) do "
+               "not match. For small hop size = ceil(audio_size / n_ir_frames), "
+               "number of impulse response frames must be a multiple of the "
+               "audio size.", n_audio_frames, F);
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (noise_fused_supported(F, nb, N, window_size)) {
+    return launch_noise_fused(mags, noise, seed, offset, audio, B, F, nb, N,
+                              window_size, accumulate, st);
+  }
+  const size_t need = ddsp_b200_filtered_noise_workspace(B, F, nb, N, window_size);
+  DDSP_REQUIRE(workspace != nullptr && workspace_bytes >= need,
+               DDSP_B200_E_WORKSPACE,
+               "filtered_noise_forward: workspace of %zu B needed, %zu given",
+               need, workspace_bytes);
+  IrGeom g = make_ir_geom(nb, window_size);
+  uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+  float* ir = reinterpret_cast<float*>(base);
+  float* nz = ir + (size_t)B * F * g.S;
+  int rc = ddsp_b200_frequency_impulse_response(mags, ir, (int64_t)B * F, nb,
+                                                window_size, stream);
+  if (rc) return rc;
+  const float* x = noise;
+  if (x == nullptr) {
+    rc = ddsp_b200_uniform_noise(nz, B, N, seed, offset, stream);
+    if (rc) return rc;
+    x = nz;
+  }
+  return ddsp_b200_fir_time_varying(x, ir, audio, B, N, F, g.S, B,
+                                    DDSP_B200_PAD_SAME, -1, accumulate, stream);
+}
+
+int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,
+                  void* stream) {
+  DDSP_REQUIRE(a && b && out, DDSP_B200_E_INVALID, "add: null pointer");
+  DDSP_REQUIRE(n >= 0, DDSP_B200_E_INVALID, "add: n < 0");
+  if (n == 0) return 0;
+  add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  DDSP_CHECK_LAUNCH("add");
+  return 0;
+}
+
+}  // extern "C"

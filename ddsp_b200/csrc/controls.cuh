@@ -1,0 +1,84 @@
+// get_controls prologues (synths.py:94-121, 165-179) and processors.Add.
+#pragma once
+#include "common.cuh"
+
+namespace ddsp {
+
+// Harmonic.get_controls: one warp per (b, f) row of harmonic_distribution.
+//   hd = exp_sigmoid(hd)                    (synths.py:110-112, core.py:386-404)
+//   hd[k] = 0 where f0 * k >= sr/2          (core.py:894-901, 888-890)
+//   hd /= sum(hd), 0 denominator -> 1e-7    (core.py:903-906, 207-210)
+__global__ void __launch_bounds__(256)
+harmonic_controls_kernel(const float* amps_in, const float* hd_in,
+                         const float* __restrict__ f0, float* amps_out,
+                         float* hd_out, int rows, int K,
+                         float nyquist, int flags) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const bool scale = flags & DDSP_B200_CTL_SCALE;
+  const bool nyq = flags & DDSP_B200_CTL_NYQUIST;
+  const float f = f0[warp];
+  const float* in = hd_in + (size_t)warp * K;
+  float* out = hd_out + (size_t)warp * K;
+  float sum = 0.f;
+  for (int c = lane; c < K; c += 32) {
+    float v = in[c];
+    if (scale) v = exp_sigmoid_f(v);
+    // get_harmonic_frequencies: f0 * linspace(1..K) in float32 (core.py:1042-1044)
+    if (nyq && __fmul_rn(f, (float)(c + 1)) >= nyquist) v = 0.f;
+    out[c] = v;
+    sum += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float denom = (sum == 0.0f) ? 1e-7f : sum;
+  for (int c = lane; c < K; c += 32) out[c] = __fdiv_rn(out[c], denom);
+  if (lane == 0) {
+    float a = amps_in[warp];
+    amps_out[warp] = scale ? exp_sigmoid_f(a) : a;
+  }
+}
+
+// FilteredNoise.get_controls: exp_sigmoid(x + initial_bias) (synths.py:176-177)
+__global__ void __launch_bounds__(256)
+noise_controls_kernel(const float* in, float* out,
+                      int64_t n, float bias, int apply_scale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = in[i];
+    out[i] = apply_scale ? exp_sigmoid_f(v + bias) : v;
+  }
+}
+
+// processors.Add.get_signal (processors.py:174-176)
+__global__ void __launch_bounds__(256)
+add_kernel(const float* a, const float* b, float* out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = a[i] + b[i];
+}
+
+// tf.random.uniform([B, N], -1, 1) stand-in (synths.py:192-193): Philox4x32-10.
+__global__ void __launch_bounds__(256)
+uniform_noise_kernel(float* __restrict__ out, int B, int N, uint64_t seed,
+                     uint64_t offset) {
+  const int n4 = (N + 3) >> 2;
+  const int64_t total = (int64_t)B * n4;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int b = (int)(i / n4);
+    const int q = (int)(i - (int64_t)b * n4);
+    const float4 v = noise4((uint32_t)q, (uint32_t)b, seed, offset);
+    float* o = out + (size_t)b * N + 4 * (size_t)q;
+    const int rem = N - 4 * q;
+    o[0] = v.x;
+    if (rem > 1) o[1] = v.y;
+    if (rem > 2) o[2] = v.z;
+    if (rem > 3) o[3] = v.w;
+  }
+}
+
+}  // namespace ddsp

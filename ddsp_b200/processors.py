@@ -1,0 +1,138 @@
+"""Processor / ProcessorGroup / Add with the reference's protocol
+(`ddsp/processors.py:37-176`) - the drop-in boundary of this library.
+
+Tensors are torch CUDA float32; the arithmetic runs in libddsp_b200.so.
+"""
+from typing import Dict, Text, Any
+
+from ddsp_b200 import core
+from ddsp_b200 import dags
+
+TensorDict = Dict[Text, Any]
+
+
+class Processor:
+  """Abstract base class for signal processors (processors.py:37-76)."""
+
+  def __init__(self, name: Text, trainable: bool = False):
+    self.name = name
+    self.trainable = trainable
+
+  def __call__(self, *args, return_outputs_dict: bool = False, **kwargs):
+    return self.call(*args, return_outputs_dict=return_outputs_dict, **kwargs)
+
+  def call(self, *args, return_outputs_dict: bool = False, **kwargs):
+    """processors.py:53-68."""
+    for k in ['training', 'mask']:
+      if k in kwargs:
+        _ = kwargs.pop(k)
+    controls = self.get_controls(*args, **kwargs)
+    signal = self.get_signal(**controls)
+    if return_outputs_dict:
+      return dict(signal=signal, controls=controls)
+    else:
+      return signal
+
+  def get_controls(self, *args, **kwargs) -> TensorDict:
+    raise NotImplementedError
+
+  def get_signal(self, *args, **kwargs):
+    raise NotImplementedError
+
+
+class ProcessorGroup(dags.DAGLayer):
+  """String Processor() objects together (processors.py:79-158)."""
+
+  def __init__(self, dag: dags.DAG, **kwarg_processors):
+    super().__init__(dag, **kwarg_processors)
+    self.processor_names = self.module_names
+
+  @property
+  def processors(self):
+    return [getattr(self, name) for name in self.processor_names]
+
+  def __call__(self, inputs: TensorDict, return_outputs_dict: bool = False,
+               **kwargs):
+    return self.call(inputs, return_outputs_dict=return_outputs_dict, **kwargs)
+
+  def call(self, inputs: TensorDict, return_outputs_dict: bool = False,
+           **kwargs):
+    """processors.py:121-131.
+
+    When only the signal is asked for and the DAG is the `ae.gin` decoder
+    (Harmonic, FilteredNoise, Add of their two signals), the three nodes run as
+    the fused pipeline (noise accumulates into the harmonic buffer: one audio
+    tensor instead of three).  With return_outputs_dict=True every node's signal
+    and controls are materialised, as the reference's contract requires.
+    """
+    if not return_outputs_dict:
+      fused = self._try_fused_decoder(inputs, **kwargs)
+      if fused is not None:
+        return fused
+    controls = self.get_controls(inputs, **kwargs)
+    signal = self.get_signal(controls)
+    if return_outputs_dict:
+      return dict(signal=signal, controls=controls)
+    else:
+      return signal
+
+  def get_controls(self, inputs: TensorDict, **kwargs) -> TensorDict:
+    """processors.py:133-146 - run the DAG, return the nested outputs dict."""
+    return super().call(inputs, **kwargs)
+
+  def get_signal(self, outputs: TensorDict):
+    """processors.py:148-158."""
+    return outputs['out']['signal']
+
+  # -- fused fast path ---------------------------------------------------------
+  def _decoder_pattern(self):
+    """Returns (harmonic, noise, harmonic_keys, noise_keys) if the DAG is
+    exactly [Harmonic(a,b,c), FilteredNoise(m), Add(two signals)], else None."""
+    from ddsp_b200 import synths  # local import: synths imports this module
+    if len(self.dag) != 3:
+      return None
+    mods = [getattr(self, node[0], None) for node in self.dag]
+    kinds = [type(m) for m in mods]
+    if kinds[2] is not Add:
+      return None
+    if kinds[:2] == [synths.Harmonic, synths.FilteredNoise]:
+      h_i, n_i = 0, 1
+    elif kinds[:2] == [synths.FilteredNoise, synths.Harmonic]:
+      h_i, n_i = 1, 0
+    else:
+      return None
+    harm, noise = mods[h_i], mods[n_i]
+    want = {f'{harm.name}/signal', f'{noise.name}/signal'}
+    if set(self.dag[2][1]) != want or len(self.dag[2][1]) != 2:
+      return None
+    if harm.n_samples != noise.n_samples:
+      return None
+    return harm, noise, list(self.dag[h_i][1]), list(self.dag[n_i][1])
+
+  def _try_fused_decoder(self, inputs, **kwargs):
+    pat = self._decoder_pattern()
+    if pat is None:
+      return None
+    harm, noise, h_keys, n_keys = pat
+    outputs = {'inputs': inputs}
+    outputs.update(inputs)
+    h_in = [core.nested_lookup(k, outputs) for k in h_keys]
+    n_in = [core.nested_lookup(k, outputs) for k in n_keys]
+    for k in ['training', 'mask']:
+      kwargs.pop(k, None)
+    audio = harm.get_signal(**harm.get_controls(*h_in, **kwargs))
+    return noise.get_signal(out=audio, accumulate=True,
+                            **noise.get_controls(*n_in, **kwargs))
+
+
+class Add(Processor):
+  """Sum two signals (processors.py:162-176)."""
+
+  def __init__(self, name: Text = 'add'):
+    super().__init__(name=name)
+
+  def get_controls(self, signal_one, signal_two) -> TensorDict:
+    return {'signal_one': signal_one, 'signal_two': signal_two}
+
+  def get_signal(self, signal_one, signal_two):
+    return core.add(signal_one, signal_two)

@@ -1,0 +1,142 @@
+/*
+ * ddsp_b200.h - C ABI of libddsp_b200.so (hand-written sm_100a kernels for the
+ * DDSP Harmonic + FilteredNoise decoder signal path).
+ *
+ * The reference (magenta/ddsp v3.7.0) has no FFI: its operator API is the Python
+ * Processor / ProcessorGroup protocol (ddsp/processors.py:37-158).  Every entry
+ * point below replaces one or more reference *functions*; the file:line each one
+ * stands for is cited.  The Python layer in ddsp_b200/ binds these with ctypes
+ * and re-creates the reference classes on top.
+ *
+ * Conventions
+ *   - All tensors are contiguous row-major float32 in DEVICE memory of the
+ *     current CUDA device.  Controls are [B, F, C]; audio is [B, N].
+ *   - The caller allocates every input, output and workspace.  The library never
+ *     allocates, frees or retains a pointer past the call.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous and
+ *     re-entrant; there is no global mutable state (the last-error string is
+ *     thread-local).
+ *   - Return value: 0 = ok, negative = DDSP_B200_E_* below.  Shape/argument
+ *     errors are detected BEFORE any launch.
+ */
+#ifndef DDSP_B200_H_
+#define DDSP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDSP_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  DDSP_B200_OK = 0,
+  DDSP_B200_E_INVALID = -1,   /* bad argument / shape (maps to ValueError)    */
+  DDSP_B200_E_UNSUPPORTED = -2, /* valid in the reference, not built here yet */
+  DDSP_B200_E_CUDA = -3,      /* CUDA runtime error (launch failed)           */
+  DDSP_B200_E_WORKSPACE = -4  /* workspace too small                          */
+};
+
+/* amp_method: how frame-rate amplitudes become audio-rate (core.py:573-714). */
+enum {
+  DDSP_B200_AMP_WINDOW = 0,   /* upsample_with_windows, Hann OLA (default)    */
+  DDSP_B200_AMP_LINEAR = 1    /* tf v1 bilinear, add_endpoint=True            */
+};
+
+/* phase_mode of the oscillator bank.  Both accumulate *wrapped* phase exactly
+ * (64-bit fixed-point turns), i.e. the intent of core.angular_cumsum
+ * (core.py:799-866); they differ only in how sin(k*phi) is evaluated. */
+enum {
+  DDSP_B200_PHASE_RECURRENCE = 0, /* Reinsch recurrence over harmonics (fast) */
+  DDSP_B200_PHASE_DIRECT = 1      /* one sin per oscillator (validation)      */
+};
+
+/* flags of ddsp_b200_harmonic_controls */
+enum {
+  DDSP_B200_CTL_SCALE = 1,            /* apply exp_sigmoid (scale_fn)          */
+  DDSP_B200_CTL_NYQUIST = 2           /* normalize_below_nyquist=True          */
+};
+
+/* padding of ddsp_b200_fir_time_varying (core.py:1338-1379) */
+enum { DDSP_B200_PAD_SAME = 0, DDSP_B200_PAD_VALID = 1 };
+
+int ddsp_b200_version(void);
+/* Thread-local description of the last non-zero return on this thread. */
+const char* ddsp_b200_last_error(void);
+/* Number of kernels this THREAD has launched through the library so far
+ * (thread-local diagnostic counter; bench.py reports it as gpu_launches). */
+uint64_t ddsp_b200_launch_count(void);
+
+/* Harmonic.get_controls (synths.py:94-121): exp_sigmoid (core.py:386-404) on
+ * amplitudes and harmonic_distribution, Nyquist mask + row normalisation
+ * (core.normalize_harmonics, core.py:894-907; safe_divide core.py:207-210).
+ * amps_in/out [B,F,1]; hd_in/out [B,F,K]; f0_hz [B,F,1]. In-place is allowed. */
+int ddsp_b200_harmonic_controls(const float* amps_in, const float* hd_in,
+                                const float* f0_hz, float* amps_out,
+                                float* hd_out, int B, int F, int K,
+                                float sample_rate, int flags, void* stream);
+
+/* Harmonic.get_signal = core.harmonic_synthesis (core.py:1048-1111) with
+ * harmonic_shifts=None: get_harmonic_frequencies (1028-1045), resample 'linear'
+ * of f0*k (573-642), resample amp*hd by amp_method (645-714), oscillator_bank
+ * (911-962) incl. audio-rate remove_above_nyquist (869-891).
+ * f0_hz [B,F,1], amps [B,F,1], hd [B,F,K] or NULL (K must be 1), audio [B,N].
+ * N must be a multiple of F.  accumulate!=0: audio += result (fused Add).    */
+int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
+                               const float* hd, float* audio, int B, int F,
+                               int K, int N, float sample_rate, int amp_method,
+                               int phase_mode, int accumulate, void* stream);
+
+/* FilteredNoise.get_controls (synths.py:165-179): exp_sigmoid(x + bias). */
+int ddsp_b200_noise_controls(const float* mag_in, float* mag_out, int64_t n,
+                             float initial_bias, int apply_scale, void* stream);
+
+/* core.frequency_impulse_response + apply_window_to_impulse_response
+ * (core.py:1534-1565, 1477-1531).  mags [BF, nb] -> ir [BF, S] with
+ * S = ddsp_b200_ir_size(nb, window_size). */
+int ddsp_b200_ir_size(int nb, int window_size);
+int ddsp_b200_frequency_impulse_response(const float* mags, float* ir,
+                                         int64_t BF, int nb, int window_size,
+                                         void* stream);
+
+/* core.fft_convolve (core.py:1382-1473) restated as the equivalent direct-form
+ * time-varying FIR (get_fft_size / rfft / irfft / overlap_and_add /
+ * crop_and_compensate_delay folded into index math).  audio [B,N]; ir
+ * [ir_batch(1 or B), F, S]; out [B, N] ('same') or [B, N+S-1] ('valid').
+ * delay_compensation < 0 -> (S-1)/2 - 1 as in the reference.
+ * accumulate!=0: out += result. */
+int ddsp_b200_fir_time_varying(const float* audio, const float* ir, float* out,
+                               int B, int N, int F, int S, int ir_batch,
+                               int padding, int delay_compensation,
+                               int accumulate, void* stream);
+
+/* Uniform noise in [-1, 1): Philox4x32-10, counter = (i/4, b, offset), key =
+ * seed.  Stands in for tf.random.uniform at synths.py:192-193. out [B,N]. */
+int ddsp_b200_uniform_noise(float* out, int B, int N, uint64_t seed,
+                            uint64_t offset, void* stream);
+
+/* FilteredNoise.get_signal (synths.py:181-196) = noise -> frequency_filter
+ * (core.py:1628-1655), fused: IRs are built in shared memory, never in HBM.
+ * mags [B,F,nb]; noise [B,N] or NULL (NULL: in-kernel Philox(seed, offset));
+ * audio [B,N].  accumulate!=0: audio += result (the fused processors.Add,
+ * processors.py:174-176).  workspace: ddsp_b200_filtered_noise_workspace()
+ * bytes (0 for the fused path; may be NULL then). */
+size_t ddsp_b200_filtered_noise_workspace(int B, int F, int nb, int N,
+                                          int window_size);
+int ddsp_b200_filtered_noise_forward(const float* mags, const float* noise,
+                                     uint64_t seed, uint64_t offset,
+                                     float* audio, int B, int F, int nb, int N,
+                                     int window_size, int accumulate,
+                                     void* workspace, size_t workspace_bytes,
+                                     void* stream);
+
+/* processors.Add.get_signal (processors.py:174-176). out may alias a or b. */
+int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDSP_B200_H_ */
