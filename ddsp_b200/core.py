@@ -89,6 +89,11 @@ def nested_lookup(nested_key: Text, nested_dict: Dict[Text, Any],
   return value
 
 
+def _shape(x):
+  """Static shape of a tensor / array / nested list, without touching a GPU."""
+  return tuple(x.shape) if hasattr(x, 'shape') else tuple(np.shape(x))
+
+
 def _stream():
   return torch.cuda.current_stream().cuda_stream
 
@@ -119,18 +124,18 @@ def harmonic_controls(amplitudes, harmonic_distribution, f0_hz, sample_rate,
                       scale=True, normalize_below_nyquist=True):
   """synths.Harmonic.get_controls arithmetic (synths.py:94-121): exp_sigmoid,
   core.normalize_harmonics (core.py:894-907)."""
+  sa, sh, sf = _shape(amplitudes), _shape(harmonic_distribution), _shape(f0_hz)
+  if len(sh) != 3 or len(sa) != 3 or len(sf) != 3:
+    raise ValueError('Harmonic controls must be 3-D [batch, frames, channels]; '
+                     f'got {sa}, {sh}, {sf}.')
+  b, f, k = sh
+  if sa != (b, f, 1) or sf != (b, f, 1):
+    raise ValueError(
+        f'amplitudes {sa} and f0_hz {sf} must be [{b}, {f}, 1] to match '
+        f'harmonic_distribution {sh}.')
   amplitudes = torch_float32(amplitudes)
   hd = torch_float32(harmonic_distribution)
   f0_hz = torch_float32(f0_hz)
-  if hd.dim() != 3 or amplitudes.dim() != 3 or f0_hz.dim() != 3:
-    raise ValueError('Harmonic controls must be 3-D [batch, frames, channels]; '
-                     f'got {tuple(amplitudes.shape)}, {tuple(hd.shape)}, '
-                     f'{tuple(f0_hz.shape)}.')
-  b, f, k = hd.shape
-  if tuple(amplitudes.shape) != (b, f, 1) or tuple(f0_hz.shape) != (b, f, 1):
-    raise ValueError(
-        f'amplitudes {tuple(amplitudes.shape)} and f0_hz {tuple(f0_hz.shape)} '
-        f'must be [{b}, {f}, 1] to match harmonic_distribution.')
   amps_out = torch.empty_like(amplitudes)
   hd_out = torch.empty_like(hd)
   flags = ((_lib.CTL_SCALE if scale else 0) |
@@ -163,10 +168,6 @@ def harmonic_synthesis(frequencies,
     raise NotImplementedError(
         'harmonic_shifts is outside the Harmonic processor path '
         '(synths.py:138-146 never passes it).')
-  frequencies = torch_float32(frequencies)
-  amplitudes = torch_float32(amplitudes)
-  if harmonic_distribution is not None:
-    harmonic_distribution = torch_float32(harmonic_distribution)
   if amp_resample_method not in ('nearest', 'linear', 'cubic', 'window'):
     # core.py:632-634
     raise ValueError('Method ({}) is invalid. Must be one of {}.'.format(
@@ -175,12 +176,22 @@ def harmonic_synthesis(frequencies,
     raise NotImplementedError(
         f"amp_resample_method='{amp_resample_method}' is not built; "
         "'window' and 'linear' are.")
-  if frequencies.dim() != 3 or amplitudes.dim() != 3:
+  sf, sa = _shape(frequencies), _shape(amplitudes)
+  if len(sf) != 3 or len(sa) != 3:
     # core.py:670-672 (the window upsampler only takes 3-D inputs)
     raise ValueError('Upsample_with_windows() only supports 3 dimensions, '
-                     'not {}.'.format(list(amplitudes.shape)))
-  b, f, _ = frequencies.shape
-  k = 1 if harmonic_distribution is None else int(harmonic_distribution.shape[-1])
+                     'not {}.'.format(list(sa)))
+  b, f, _ = sf
+  if sa != (b, f, 1) or sf != (b, f, 1):
+    raise ValueError(f'frequencies {sf} and amplitudes {sa} must both be '
+                     f'[batch, n_frames, 1].')
+  k = 1
+  if harmonic_distribution is not None:
+    sh = _shape(harmonic_distribution)
+    if len(sh) != 3 or sh[:2] != (b, f):
+      raise ValueError(f'harmonic_distribution {sh} must be [{b}, {f}, '
+                       'n_harmonics].')
+    k = int(sh[-1])
   n_samples = int(n_samples)
   if amp_resample_method == 'window':
     if f >= n_samples:
@@ -194,12 +205,20 @@ def harmonic_synthesis(frequencies,
           'For upsampling, the target the number of timesteps must be divisible '
           'by the number of input frames{}. (timesteps:{}, frames:{}, '
           'add_endpoint={}).'.format('', n_samples, f + 1, True))
+  if n_samples % f != 0:
+    raise NotImplementedError(
+        f'n_samples ({n_samples}) must be a multiple of the number of frames '
+        f'({f}): non-integer hops are not built.')
+  mode = {'recurrence': _lib.PHASE_RECURRENCE, 'direct': _lib.PHASE_DIRECT}[
+      phase_mode]
+  frequencies = torch_float32(frequencies)
+  amplitudes = torch_float32(amplitudes)
+  if harmonic_distribution is not None:
+    harmonic_distribution = torch_float32(harmonic_distribution)
   if out is None:
     out = torch.empty((b, n_samples), dtype=torch.float32,
                       device=frequencies.device)
     accumulate = False
-  mode = {'recurrence': _lib.PHASE_RECURRENCE, 'direct': _lib.PHASE_DIRECT}[
-      phase_mode]
   _lib.check(_lib.load().ddsp_b200_harmonic_forward(
       _ptr(frequencies), _ptr(amplitudes), _ptr(harmonic_distribution),
       _ptr(out), b, f, k, n_samples, float(sample_rate),
@@ -220,12 +239,12 @@ def get_fft_size(frame_size: int, ir_size: int, power_of_2: bool = True) -> int:
 
 def frequency_impulse_response(magnitudes, window_size: int = 0):
   """core.frequency_impulse_response (core.py:1534-1565)."""
-  magnitudes = torch_float32(magnitudes)
-  nb = int(magnitudes.shape[-1])
+  nb = int(_shape(magnitudes)[-1])
   lib = _lib.load()
   s = lib.ddsp_b200_ir_size(nb, int(window_size))
   if s < 0:
     raise ValueError(f'frequency_impulse_response needs >= 2 frequencies, got {nb}.')
+  magnitudes = torch_float32(magnitudes)
   ir = torch.empty(tuple(magnitudes.shape[:-1]) + (s,), dtype=torch.float32,
                    device=magnitudes.device)
   bf = magnitudes.numel() // nb
@@ -260,12 +279,14 @@ def fft_convolve(audio, impulse_response, padding: Text = 'same',
   (frame / rfft / multiply / irfft / overlap_and_add / crop folded into index
   math) - the name is kept for drop-in compatibility.
   """
-  audio = torch_float32(audio)
-  impulse_response = torch_float32(impulse_response)
-  batch_size, audio_size = audio.shape
-  if impulse_response.dim() == 2:
-    impulse_response = impulse_response[:, None, :]
-  ir_batch, n_ir_frames, ir_size = impulse_response.shape
+  sa, si = _shape(audio), _shape(impulse_response)
+  if len(sa) != 2 or len(si) not in (2, 3):
+    raise ValueError(f'audio must be [batch, time] and impulse_response 2-D or '
+                     f'3-D; got {sa} and {si}.')
+  batch_size, audio_size = sa
+  if len(si) == 2:
+    si = (si[0], 1, si[1])
+  ir_batch, n_ir_frames, ir_size = si
   if not (ir_batch == 1 and batch_size > 1) and batch_size != ir_batch:
     # core.py:1441-1443
     raise ValueError('Batch size of audio ({}) and impulse response ({}) must '
@@ -288,11 +309,12 @@ def fft_convolve(audio, impulse_response, padding: Text = 'same',
     # end == 0 yields an empty tensor).  Reproduce the empty case; refuse the
     # rest rather than guess.
     if out_len == 0:
-      return torch.empty((batch_size, 0), dtype=torch.float32,
-                         device=audio.device)
+      return torch.empty((batch_size, 0), dtype=torch.float32, device=_device())
     raise NotImplementedError(
         'crop_and_compensate_delay slice is degenerate for this shape '
         f'(start={start}, total={total_size}, crop={crop_size}).')
+  audio = torch_float32(audio)
+  impulse_response = torch_float32(impulse_response).reshape(si)
   if out is None:
     out = torch.empty((batch_size, crop_size), dtype=torch.float32,
                       device=audio.device)
@@ -328,18 +350,27 @@ def filtered_noise(magnitudes, n_samples, window_size=257, noise=None, seed=0,
                    offset=0, out=None, accumulate=False):
   """FilteredNoise.get_signal arithmetic (synths.py:181-196): uniform noise ->
   core.frequency_filter (core.py:1628-1655), fused where the shape allows."""
-  magnitudes = torch_float32(magnitudes)
-  if magnitudes.dim() != 3:
+  sm = _shape(magnitudes)
+  if len(sm) != 3:
     raise ValueError('magnitudes must be [batch, n_frames, n_filter_banks], got '
-                     f'{tuple(magnitudes.shape)}.')
-  b, f, nb = magnitudes.shape
+                     f'{sm}.')
+  b, f, nb = sm
   n_samples = int(n_samples)
+  if noise is not None and _shape(noise) != (b, n_samples):
+    raise ValueError(f'noise must be [{b}, {n_samples}], got {_shape(noise)}.')
+  frame_size = int(np.ceil(n_samples / f))
+  n_audio_frames = -(-n_samples // frame_size)
+  if n_audio_frames != f:
+    # core.py:1452-1457
+    raise ValueError(
+        'Number of Audio frames ({}) and impulse response frames ({}) do not '
+        'match. For small hop size = ceil(audio_size / n_ir_frames), '
+        'number of impulse response frames must be a multiple of the audio '
+        'size.'.format(n_audio_frames, f))
+  lib = _lib.load()
+  magnitudes = torch_float32(magnitudes)
   if noise is not None:
     noise = torch_float32(noise)
-    if tuple(noise.shape) != (b, n_samples):
-      raise ValueError(f'noise must be [{b}, {n_samples}], got '
-                       f'{tuple(noise.shape)}.')
-  lib = _lib.load()
   if out is None:
     out = torch.empty((b, n_samples), dtype=torch.float32,
                       device=magnitudes.device)

@@ -1,7 +1,400 @@
-// Fast path of the harmonic kernel (hop % 64 == 0).  Placeholder until built.
+// Fast path of the fused harmonic kernel for hop % 64 == 0 (every reference
+// config: hop = 64).  Same maths as harmonic.cuh; what changes is the mapping:
+//
+//   * one warp owns one frame at a time; a lane owns samples (r, r + 32) of a
+//     64-sample chunk, so the two frame rows x0 = hd[i], x1 = hd[i+1] are
+//     warp-uniform and come from shared memory as broadcast 128-bit loads;
+//   * the frame slab hd[i0 .. i0+FT] is staged with ONE 1-D TMA bulk copy
+//     (cp.async.bulk + mbarrier) when the rows are 16-byte multiples;
+//   * sin(k phi) for k = 1..K comes from two interleaved Reinsch recurrences
+//     (odd / even harmonics, angle 2 phi reduced to [-pi/2, pi/2]) held as one
+//     packed f32x2 chain, so a harmonic pair costs 2 FFMA2 + 1 FFMA2 + 1 FADD2
+//     per sample; amplitudes are NOT interpolated per oscillator - the two
+//     frame rows get their own accumulators and the Hann / linear weights are
+//     applied once per sample:  sum_k (w0 x0_k + w1 x1_k) s_k
+//                             = w0 sum_k x0_k s_k + w1 sum_k x1_k s_k;
+//   * the audio-rate Nyquist mask (core.py:942) is a per-sample live count;
+//     harmonics below the warp-wide minimum run unmasked, the few between
+//     min and max run with a per-lane predicate.
 #pragma once
 #include "harmonic.cuh"
+
 namespace ddsp {
-inline bool harmonic_fast_supported(const HarmonicParams&) { return false; }
-inline int launch_harmonic_fast(const HarmonicParams&, cudaStream_t) { return 1; }
+
+constexpr int kFastThreads = 256;
+constexpr int kSinTabBits = 8;
+constexpr int kSinTab = 1 << kSinTabBits;  // 256-entry (sin, cos) table
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  return __ffma2_rn(a, b, c);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  return __fadd2_rn(a, b);
+}
+
+struct FastSmem {
+  size_t off_P, off_A, off_D, off_red, off_mbar, off_f0, off_amp, off_kc,
+      off_w, off_tab, off_x, total;
+};
+
+__host__ __device__ inline FastSmem fast_smem_layout(int FT, int Kp, int hop) {
+  FastSmem s;
+  size_t o = 0;
+  s.off_P = o;    o += sizeof(unsigned long long) * FT;
+  s.off_A = o;    o += sizeof(unsigned long long) * FT;
+  s.off_D = o;    o += sizeof(unsigned long long) * FT;
+  s.off_red = o;  o += sizeof(unsigned long long) * 8;
+  o = (o + 15) & ~(size_t)15;
+  s.off_mbar = o; o += 16;
+  s.off_tab = o;  o += sizeof(float2) * kSinTab;
+  s.off_x = o;    o += sizeof(float) * (size_t)(FT + 1) * Kp;   // 16 B aligned
+  s.off_f0 = o;   o += sizeof(float) * (FT + 1);
+  s.off_amp = o;  o += sizeof(float) * (FT + 1);
+  s.off_kc = o;   o += sizeof(int) * 2 * FT;
+  s.off_w = o;    o += sizeof(float) * hop;
+  s.total = (o + 15) & ~(size_t)15;
+  return s;
+}
+
+// --- mbarrier / TMA bulk copy (PTX) -----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src,
+                                             uint32_t bytes, void* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+// Slow, exact per-oscillator evaluation of one sample (frames with f0 < 1 Hz,
+// where the live-count shortcut is not valid).
+__device__ __noinline__ float harmonic_sample_exact(const float* x0,
+                                                    const float* x1, float w0,
+                                                    float w1, uint32_t p32,
+                                                    float f_lo, float f_hi,
+                                                    float frac, int K,
+                                                    float nyq) {
+  float acc = 0.f;
+  uint32_t pk = 0;
+  for (int k = 1; k <= K; ++k) {
+    pk += p32;
+    if (!(ref_harmonic_freq(f_lo, f_hi, frac, k) < nyq)) continue;
+    float a = x0[k - 1] * w0 + x1[k - 1] * w1;
+    acc = fmaf(a, sinpif((float)(int)pk * 4.656612873077393e-10f), acc);
+  }
+  return acc;
+}
+
+// Per-sample oscillator state for the packed recurrence.
+struct OscState {
+  float2 v;      // (sin((1+2j) phi), sin((2+2j) phi)) up to the (-1)^j flip
+  float2 d;      // v_j - v_{j-1}
+  float2 nalpha; // (-alpha, -alpha), alpha = 4 sin^2(Phi_eff / 2)
+  float2 e0, e1, o0, o1;  // accumulators: row x0/x1, even/odd j
+  float sigma;   // +1, or -1 if the chain angle was shifted by half a turn
+};
+
+__device__ __forceinline__ void osc_init(OscState& st, uint32_t p32,
+                                         const float2* __restrict__ tab) {
+  // sin/cos of the fundamental phase: table (top bits) + 3rd-order correction
+  const uint32_t idx = (p32 + (1u << (31 - kSinTabBits))) >> (32 - kSinTabBits);
+  const int resid = (int)(p32 - (idx << (32 - kSinTabBits)));   // signed
+  const float eps = (float)resid * 1.4629180792671596e-9f;      // 2 pi / 2^32
+  const float2 sc = tab[idx & (kSinTab - 1)];
+  const float e2 = eps * eps;
+  // sin(a+e) = S (1 - e^2/2) + C e (1 - e^2/6);  cos(a+e) = C (1 - e^2/2) - S e (1 - e^2/6)
+  const float ce = fmaf(e2, -0.5f, 1.0f);
+  const float se = eps * fmaf(e2, -0.16666667f, 1.0f);
+  const float s1 = fmaf(sc.y, se, sc.x * ce);
+  const float c1 = fmaf(-sc.x, se, sc.y * ce);
+  const float ss = s1 * s1, cc = c1 * c1;
+  const bool flip = ss > cc;                 // cos(2 phi) < 0
+  const float alpha = 4.0f * fminf(ss, cc);
+  const float s2 = 2.0f * s1 * c1;
+  st.v = make_float2(s1, s2);
+  st.d = make_float2(flip ? 0.0f : 2.0f * s1, s2);
+  st.nalpha = make_float2(-alpha, -alpha);
+  st.sigma = flip ? -1.0f : 1.0f;
+  st.e0 = st.e1 = st.o0 = st.o1 = make_float2(0.f, 0.f);
+}
+
+// Advance the chain by one step (two harmonics).
+__device__ __forceinline__ void osc_step(OscState& st) {
+  st.d = ffma2(st.nalpha, st.v, st.d);
+  st.v = fadd2(st.v, st.d);
+}
+
+template <bool WINDOW>
+__global__ void __launch_bounds__(kFastThreads)
+harmonic_fast_kernel(HarmonicParams p, int use_tma) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int FT = p.FT, Kp = p.Kp, K = p.K, F = p.F, hop = p.hop;
+  const FastSmem L = fast_smem_layout(FT, Kp, hop);
+  unsigned long long* sP = (unsigned long long*)(smem_raw + L.off_P);
+  unsigned long long* sA = (unsigned long long*)(smem_raw + L.off_A);
+  unsigned long long* sD = (unsigned long long*)(smem_raw + L.off_D);
+  unsigned long long* sRed = (unsigned long long*)(smem_raw + L.off_red);
+  void* mbar = (void*)(smem_raw + L.off_mbar);
+  float2* sTab = (float2*)(smem_raw + L.off_tab);
+  float* sX = (float*)(smem_raw + L.off_x);
+  float* sF0 = (float*)(smem_raw + L.off_f0);
+  float* sAmp = (float*)(smem_raw + L.off_amp);
+  int* sKc = (int*)(smem_raw + L.off_kc);
+  float* sW = (float*)(smem_raw + L.off_w);
+
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * FT;
+  const int nfr = min(FT, F - i0);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const float* f0b = p.f0 + (size_t)b * F;
+  const float* ampb = p.amps + (size_t)b * F;
+  const int rows_in = min(nfr + 1, F - i0);
+
+  // ---- 0. kick off the slab copy ----
+  if (use_tma) {
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)rows_in * (uint32_t)K * 4u;
+      mbar_expect_tx(mbar, bytes);
+      tma_bulk_g2s(sX, p.hd + ((size_t)b * F + i0) * K, bytes, mbar);
+    }
+  }
+
+  // ---- 1. wrapping prefix of frame phase totals before this tile ----
+  unsigned long long part = 0;
+  for (int j = tid; j < i0; j += kFastThreads) {
+    double a0 = (double)f0b[j] * p.inv_sr;
+    double a1 = (double)f0b[min(j + 1, F - 1)] * p.inv_sr;
+    part += turns_to_fix64((double)hop * a0 + (a1 - a0) * (0.5 * (hop - 1)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) sRed[warp] = part;
+
+  // ---- 2. small tables ----
+  for (int j = tid; j <= nfr; j += kFastThreads) {
+    int g = min(i0 + j, F - 1);
+    sF0[j] = f0b[g];
+    sAmp[j] = ampb[g];
+  }
+  for (int j = tid; j < kSinTab; j += kFastThreads) {
+    float s, c;
+    sincospif(2.0f * (float)j / (float)kSinTab, &s, &c);
+    sTab[j] = make_float2(s, c);
+  }
+  {
+    const float inv_hop = 1.0f / (float)hop;
+    for (int r = tid; r < hop; r += kFastThreads) {
+      const float frac = (float)r * inv_hop;
+      sW[r] = WINDOW ? (0.5f - 0.5f * cospif(frac)) : frac;
+    }
+  }
+  if (!use_tma) {
+    if (p.hd != nullptr) {
+      const float* hdb = p.hd + ((size_t)b * F + i0) * K;
+      for (int idx = tid; idx < rows_in * Kp; idx += kFastThreads) {
+        int r = idx / Kp, c = idx - r * Kp;
+        sX[idx] = (c < K) ? hdb[r * K + c] : 0.f;
+      }
+    } else {
+      for (int idx = tid; idx < rows_in * Kp; idx += kFastThreads)
+        sX[idx] = (idx % Kp == 0) ? 1.0f : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. per-frame phase tables + live counts at the frame ends ----
+  if (tid == 0) {
+    unsigned long long P = 0;
+    for (int w = 0; w < kFastThreads / 32; ++w) P += sRed[w];
+    for (int j = 0; j < nfr; ++j) {
+      double a0 = (double)sF0[j] * p.inv_sr;
+      double a1 = (double)sF0[j + 1] * p.inv_sr;
+      sP[j] = P;
+      sA[j] = turns_to_fix64(a0);
+      sD[j] = turns_to_fix64((a1 - a0) / (double)hop);
+      P += turns_to_fix64((double)hop * a0 + (a1 - a0) * (0.5 * (hop - 1)));
+    }
+  }
+  for (int j = tid; j < nfr; j += kFastThreads) {
+    const float f_lo = sF0[j], f_hi = sF0[j + 1];
+    if (f_lo >= 1.0f && f_hi >= 1.0f) {
+      sKc[2 * j] = live_harmonics(f_lo, f_hi, 0.0f, K, p.nyquist);
+      sKc[2 * j + 1] = live_harmonics(
+          f_lo, f_hi, (float)(hop - 1) * (1.0f / (float)hop), K, p.nyquist);
+    } else {
+      sKc[2 * j] = sKc[2 * j + 1] = -1;   // exact slow path
+    }
+  }
+  if (use_tma) mbar_wait(mbar, 0);
+  __syncthreads();
+  if (rows_in < nfr + 1) {                    // frame F := frame F-1
+    for (int c = tid; c < Kp; c += kFastThreads)
+      sX[nfr * Kp + c] = sX[(nfr - 1) * Kp + c];
+    __syncthreads();
+  }
+
+  // ---- 4. samples: warp w takes frames w, w+8, ...; 64 samples per pass ----
+  const float inv_hop = 1.0f / (float)hop;
+  float* outb = p.audio + (size_t)b * p.N + (size_t)i0 * hop;
+  for (int li = warp; li < nfr; li += kFastThreads / 32) {
+    const float f_lo = sF0[li], f_hi = sF0[li + 1];
+    const float amp0 = sAmp[li], amp1 = sAmp[li + 1];
+    const unsigned long long Pi = sP[li], Ai = sA[li], Di = sD[li];
+    const int kc_a = sKc[2 * li], kc_b = sKc[2 * li + 1];
+    const float* x0 = sX + li * Kp;
+    const float* x1 = x0 + Kp;
+    for (int r0 = 0; r0 < hop; r0 += 64) {
+      const int ra = r0 + lane, rb = ra + 32;
+      // fundamental phase, 64-bit fixed point turns (inclusive cumsum)
+      const unsigned long long pha = Pi + (unsigned long long)(ra + 1) * Ai +
+          (unsigned long long)(((long long)ra * (ra + 1)) >> 1) * Di;
+      const unsigned long long phb = Pi + (unsigned long long)(rb + 1) * Ai +
+          (unsigned long long)(((long long)rb * (rb + 1)) >> 1) * Di;
+      const uint32_t pa = (uint32_t)((pha + 0x80000000ull) >> 32);
+      const uint32_t pb = (uint32_t)((phb + 0x80000000ull) >> 32);
+      const float w1a_ = sW[ra], w1b_ = sW[rb];
+      const float w0a = (1.0f - w1a_) * amp0, w1a = w1a_ * amp1;
+      const float w0b = (1.0f - w1b_) * amp0, w1b = w1b_ * amp1;
+      float ya, yb;
+      if (kc_a < 0) {
+        ya = harmonic_sample_exact(x0, x1, w0a, w1a, pa, f_lo, f_hi,
+                                   (float)ra * inv_hop, K, p.nyquist);
+        yb = harmonic_sample_exact(x0, x1, w0b, w1b, pb, f_lo, f_hi,
+                                   (float)rb * inv_hop, K, p.nyquist);
+      } else {
+        int ka = kc_a, kb = kc_a, kmin = kc_a, kmax = kc_a;
+        if (kc_a != kc_b) {      // live count changes inside this frame
+          ka = live_harmonics(f_lo, f_hi, (float)ra * inv_hop, K, p.nyquist);
+          kb = live_harmonics(f_lo, f_hi, (float)rb * inv_hop, K, p.nyquist);
+          kmin = __reduce_min_sync(0xffffffffu, min(ka, kb));
+          kmax = __reduce_max_sync(0xffffffffu, max(ka, kb));
+        }
+        OscState A, Bs;
+        osc_init(A, pa, sTab);
+        osc_init(Bs, pb, sTab);
+        const int k_main = kmin & ~3;            // harmonics 1..k_main unmasked
+        int k = 0;
+        for (; k < k_main; k += 4) {
+          const float4 X0 = *reinterpret_cast<const float4*>(x0 + k);
+          const float4 X1 = *reinterpret_cast<const float4*>(x1 + k);
+          const float2 x0l = make_float2(X0.x, X0.y), x0h = make_float2(X0.z, X0.w);
+          const float2 x1l = make_float2(X1.x, X1.y), x1h = make_float2(X1.z, X1.w);
+          A.e0 = ffma2(x0l, A.v, A.e0);   A.e1 = ffma2(x1l, A.v, A.e1);
+          Bs.e0 = ffma2(x0l, Bs.v, Bs.e0); Bs.e1 = ffma2(x1l, Bs.v, Bs.e1);
+          osc_step(A); osc_step(Bs);
+          A.o0 = ffma2(x0h, A.v, A.o0);   A.o1 = ffma2(x1h, A.v, A.o1);
+          Bs.o0 = ffma2(x0h, Bs.v, Bs.o0); Bs.o1 = ffma2(x1h, Bs.v, Bs.o1);
+          osc_step(A); osc_step(Bs);
+        }
+        for (; k < kmax; k += 4) {               // masked tail (<= 2 passes)
+          const float4 X0 = *reinterpret_cast<const float4*>(x0 + k);
+          const float4 X1 = *reinterpret_cast<const float4*>(x1 + k);
+          // harmonic numbers k+1 .. k+4; live iff number <= ka / kb
+          const float2 mal = make_float2(k + 1 <= ka ? 1.f : 0.f, k + 2 <= ka ? 1.f : 0.f);
+          const float2 mah = make_float2(k + 3 <= ka ? 1.f : 0.f, k + 4 <= ka ? 1.f : 0.f);
+          const float2 mbl = make_float2(k + 1 <= kb ? 1.f : 0.f, k + 2 <= kb ? 1.f : 0.f);
+          const float2 mbh = make_float2(k + 3 <= kb ? 1.f : 0.f, k + 4 <= kb ? 1.f : 0.f);
+          const float2 x0l = make_float2(X0.x, X0.y), x0h = make_float2(X0.z, X0.w);
+          const float2 x1l = make_float2(X1.x, X1.y), x1h = make_float2(X1.z, X1.w);
+          float2 va = make_float2(A.v.x * mal.x, A.v.y * mal.y);
+          float2 vb = make_float2(Bs.v.x * mbl.x, Bs.v.y * mbl.y);
+          A.e0 = ffma2(x0l, va, A.e0);   A.e1 = ffma2(x1l, va, A.e1);
+          Bs.e0 = ffma2(x0l, vb, Bs.e0); Bs.e1 = ffma2(x1l, vb, Bs.e1);
+          osc_step(A); osc_step(Bs);
+          va = make_float2(A.v.x * mah.x, A.v.y * mah.y);
+          vb = make_float2(Bs.v.x * mbh.x, Bs.v.y * mbh.y);
+          A.o0 = ffma2(x0h, va, A.o0);   A.o1 = ffma2(x1h, va, A.o1);
+          Bs.o0 = ffma2(x0h, vb, Bs.o0); Bs.o1 = ffma2(x1h, vb, Bs.o1);
+          osc_step(A); osc_step(Bs);
+        }
+        {
+          const float r0a = (A.e0.x + A.e0.y) + A.sigma * (A.o0.x + A.o0.y);
+          const float r1a = (A.e1.x + A.e1.y) + A.sigma * (A.o1.x + A.o1.y);
+          ya = r0a * w0a + r1a * w1a;
+          const float r0b = (Bs.e0.x + Bs.e0.y) + Bs.sigma * (Bs.o0.x + Bs.o0.y);
+          const float r1b = (Bs.e1.x + Bs.e1.y) + Bs.sigma * (Bs.o1.x + Bs.o1.y);
+          yb = r0b * w0b + r1b * w1b;
+        }
+      }
+      float* o = outb + (size_t)li * hop + r0;
+      if (p.accumulate) {
+        ya += o[lane];
+        yb += o[lane + 32];
+      }
+      o[lane] = ya;
+      o[lane + 32] = yb;
+    }
+  }
+}
+
+inline bool harmonic_fast_supported(const HarmonicParams& p) {
+  return (p.hop % 64 == 0) && p.hop <= 8192 && p.K <= 1024;
+}
+
+// Returns 0 on success, negative on error, 1 if it declines (caller falls back).
+inline int launch_harmonic_fast(HarmonicParams p, cudaStream_t st) {
+  p.Kp = (p.K + 3) & ~3;
+  int FT = std::max(1, 2048 / p.hop);
+  const long long want_ctas = 4ll * kNumSMs;
+  int ft_fill = (int)std::max<long long>(1, ((long long)p.B * p.F + want_ctas - 1) / want_ctas);
+  FT = std::min(FT, std::max(ft_fill, std::min(8, p.F)));
+  FT = std::min(FT, p.F);
+  while (FT > 1 && fast_smem_layout(FT, p.Kp, p.hop).total > 100 * 1024) FT = (FT + 1) / 2;
+  const size_t smem = fast_smem_layout(FT, p.Kp, p.hop).total;
+  if (smem > 200 * 1024) return 1;
+  p.FT = FT;
+  // TMA bulk copy needs 16-byte aligned rows and base
+  const int use_tma = (p.hd != nullptr) && (p.K % 4 == 0) &&
+                      (((uintptr_t)p.hd & 15) == 0);
+  dim3 grid((p.F + FT - 1) / FT, p.B);
+  cudaError_t e;
+  if (p.amp_method == DDSP_B200_AMP_WINDOW) {
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(harmonic_fast_kernel<true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return 1;
+    }
+    harmonic_fast_kernel<true><<<grid, kFastThreads, smem, st>>>(p, use_tma);
+  } else {
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(harmonic_fast_kernel<false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return 1;
+    }
+    harmonic_fast_kernel<false><<<grid, kFastThreads, smem, st>>>(p, use_tma);
+  }
+  DDSP_CHECK_LAUNCH("harmonic_forward(fast)");
+  return 0;
+}
+
 }  // namespace ddsp
