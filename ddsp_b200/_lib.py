@@ -53,6 +53,9 @@ SIGNATURES = {
     'ddsp_b200_filtered_noise_forward':
         (_i, [_vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz,
               _vp]),
+    'ddsp_b200_decoder_forward':
+        (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _f,
+              _i, _i, _i, _f, _vp]),
     'ddsp_b200_add': (_i, [_vp, _vp, _vp, _i64, _vp]),
 }
 

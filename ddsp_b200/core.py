@@ -387,6 +387,45 @@ def filtered_noise(magnitudes, n_samples, window_size=257, noise=None, seed=0,
   return out
 
 
+def decoder_forward(amps, harmonic_distribution, f0_hz, noise_magnitudes,
+                    n_samples, sample_rate=16000, amp_resample_method='window',
+                    normalize_below_nyquist=True, window_size=0,
+                    initial_bias=-5.0, noise=None, seed=0, offset=0):
+  """The `ae.gin` DAG (ae.gin:47-72) from RAW network outputs, two launches:
+  Harmonic (exp_sigmoid scaling + Nyquist normalisation fused into the tile
+  staging) then FilteredNoise (exp_sigmoid fused likewise) accumulating into the
+  same audio buffer (= processors.Add).  Raises NotImplementedError outside the
+  fused regime; ProcessorGroup then runs the per-processor path."""
+  sh = _shape(harmonic_distribution)
+  sm = _shape(noise_magnitudes)
+  if len(sh) != 3 or len(sm) != 3:
+    raise ValueError(f'decoder inputs must be 3-D, got {sh} and {sm}.')
+  b, f, k = sh
+  if _shape(amps) != (b, f, 1) or _shape(f0_hz) != (b, f, 1) or sm[:2] != (b, f):
+    raise ValueError(
+        f'decoder inputs disagree: amps {_shape(amps)}, f0_hz {_shape(f0_hz)}, '
+        f'harmonic_distribution {sh}, noise_magnitudes {sm}.')
+  if amp_resample_method not in AMP_METHODS:
+    raise NotImplementedError(amp_resample_method)
+  n_samples = int(n_samples)
+  if noise is not None and _shape(noise) != (b, n_samples):
+    raise ValueError(f'noise must be [{b}, {n_samples}], got {_shape(noise)}.')
+  amps = torch_float32(amps)
+  hd = torch_float32(harmonic_distribution)
+  f0_hz = torch_float32(f0_hz)
+  mags = torch_float32(noise_magnitudes)
+  if noise is not None:
+    noise = torch_float32(noise)
+  out = torch.empty((b, n_samples), dtype=torch.float32, device=hd.device)
+  flags = _lib.CTL_SCALE | (_lib.CTL_NYQUIST if normalize_below_nyquist else 0)
+  _lib.check(_lib.load().ddsp_b200_decoder_forward(
+      _ptr(amps), _ptr(hd), _ptr(f0_hz), _ptr(mags), _ptr(noise),
+      int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _ptr(out), b, f, k,
+      sm[2], n_samples, float(sample_rate), AMP_METHODS[amp_resample_method],
+      flags, int(window_size), float(initial_bias), _stream()))
+  return out
+
+
 def noise_controls(magnitudes, initial_bias=-5.0, scale=True):
   """FilteredNoise.get_controls arithmetic (synths.py:165-179)."""
   magnitudes = torch_float32(magnitudes)

@@ -123,6 +123,7 @@ int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
   p.inv_sr = 1.0 / (double)sample_rate;
   p.amp_method = amp_method;
   p.accumulate = accumulate;
+  p.ctl_flags = 0;
   cudaStream_t st = (cudaStream_t)stream;
 
   if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_fast_supported(p)) {
@@ -310,6 +311,58 @@ int ddsp_b200_filtered_noise_forward(const float* mags, const float* noise,
   }
   return ddsp_b200_fir_time_varying(x, ir, audio, B, N, F, g.S, B,
                                     DDSP_B200_PAD_SAME, -1, accumulate, stream);
+}
+
+int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
+                              const float* f0_hz, const float* mags_raw,
+                              const float* noise, uint64_t seed, uint64_t offset,
+                              float* audio, int B, int F, int K, int nb, int N,
+                              float sample_rate, int amp_method,
+                              int harmonic_flags, int window_size,
+                              float initial_bias, void* stream) {
+  DDSP_REQUIRE(amps_raw && hd_raw && f0_hz && mags_raw && audio,
+               DDSP_B200_E_INVALID, "decoder_forward: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && K >= 1 && N >= 1 && nb >= 2,
+               DDSP_B200_E_INVALID,
+               "decoder_forward: bad shape B=%d F=%d K=%d nb=%d N=%d", B, F, K,
+               nb, N);
+  DDSP_REQUIRE(amp_method == DDSP_B200_AMP_WINDOW ||
+                   amp_method == DDSP_B200_AMP_LINEAR,
+               DDSP_B200_E_INVALID, "decoder_forward: bad amp_method %d",
+               amp_method);
+  DDSP_REQUIRE(harmonic_flags != 0 &&
+                   (harmonic_flags & ~(DDSP_B200_CTL_SCALE | DDSP_B200_CTL_NYQUIST)) == 0,
+               DDSP_B200_E_INVALID, "decoder_forward: bad harmonic_flags %d",
+               harmonic_flags);
+  DDSP_REQUIRE(sample_rate > 0.f, DDSP_B200_E_INVALID,
+               "decoder_forward: sample_rate must be positive");
+  if (B == 0) return 0;
+  HarmonicParams p;
+  p.f0 = f0_hz; p.amps = amps_raw; p.hd = hd_raw; p.audio = audio;
+  p.B = B; p.F = F; p.K = K; p.N = N; p.hop = N / F;
+  p.sample_rate = sample_rate;
+  p.nyquist = sample_rate * 0.5f;
+  p.inv_sr = 1.0 / (double)sample_rate;
+  p.amp_method = amp_method;
+  p.accumulate = 0;
+  p.ctl_flags = harmonic_flags;
+  // The single-pass pipeline exists for the decoder regime only; everything
+  // else goes through get_controls + the two *_forward calls.
+  DDSP_REQUIRE(N % F == 0 && B <= 65535 && harmonic_fast_supported(p) &&
+                   noise_fused_supported(F, nb, N, window_size),
+               DDSP_B200_E_UNSUPPORTED,
+               "decoder_forward: shape outside the fused decoder path "
+               "(needs hop %% 64 == 0, n_frequencies <= %d)", kNfMaxNb);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_harmonic_fast(p, st);
+  if (rc == 1) {
+    set_error("decoder_forward: harmonic tile does not fit shared memory");
+    return DDSP_B200_E_UNSUPPORTED;
+  }
+  if (rc) return rc;
+  return launch_noise_fused(mags_raw, noise, seed, offset, audio, B, F, nb, N,
+                            window_size, /*accumulate=*/1, st, /*raw=*/1,
+                            initial_bias);
 }
 
 int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,

@@ -32,6 +32,10 @@ struct HarmonicParams {
   double inv_sr;
   int amp_method;
   int accumulate;
+  // 0: amps / hd are synthesizer CONTROLS (outputs of get_controls).
+  // DDSP_B200_CTL_*: they are raw network outputs; Harmonic.get_controls
+  // (synths.py:94-121) is applied while the frame slab is staged (fast path).
+  int ctl_flags;
 };
 
 // The reference's float32 evaluation of the k-th harmonic's audio-rate

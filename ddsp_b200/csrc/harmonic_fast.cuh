@@ -201,10 +201,12 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   if (lane == 0) sRed[warp] = part;
 
   // ---- 2. small tables ----
+  const bool raw_scale = p.ctl_flags & DDSP_B200_CTL_SCALE;
   for (int j = tid; j <= nfr; j += kFastThreads) {
     int g = min(i0 + j, F - 1);
     sF0[j] = f0b[g];
-    sAmp[j] = ampb[g];
+    const float a = ampb[g];
+    sAmp[j] = raw_scale ? exp_sigmoid_f(a) : a;     // synths.py:110-111
   }
   for (int j = tid; j < kSinTab; j += kFastThreads) {
     float s, c;
@@ -233,16 +235,29 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   __syncthreads();
 
   // ---- 3. per-frame phase tables + live counts at the frame ends ----
-  if (tid == 0) {
+  // Frame totals are scanned with wrapping 64-bit adds (exact, associative), 32
+  // frames per warp pass; P_i = tile prefix + exclusive scan of the totals.
+  if (warp == 0) {
     unsigned long long P = 0;
     for (int w = 0; w < kFastThreads / 32; ++w) P += sRed[w];
-    for (int j = 0; j < nfr; ++j) {
-      double a0 = (double)sF0[j] * p.inv_sr;
-      double a1 = (double)sF0[j + 1] * p.inv_sr;
-      sP[j] = P;
-      sA[j] = turns_to_fix64(a0);
-      sD[j] = turns_to_fix64((a1 - a0) / (double)hop);
-      P += turns_to_fix64((double)hop * a0 + (a1 - a0) * (0.5 * (hop - 1)));
+    for (int base = 0; base < nfr; base += 32) {
+      const int j = base + lane;
+      unsigned long long tot = 0;
+      if (j < nfr) {
+        const double a0 = (double)sF0[j] * p.inv_sr;
+        const double a1 = (double)sF0[j + 1] * p.inv_sr;
+        sA[j] = turns_to_fix64(a0);
+        sD[j] = turns_to_fix64((a1 - a0) / (double)hop);
+        tot = turns_to_fix64((double)hop * a0 + (a1 - a0) * (0.5 * (hop - 1)));
+      }
+      unsigned long long incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (j < nfr) sP[j] = P + (incl - tot);
+      P += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
   for (int j = tid; j < nfr; j += kFastThreads) {
@@ -257,6 +272,29 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   }
   if (use_tma) mbar_wait(mbar, 0);
   __syncthreads();
+  if (p.ctl_flags != 0 && p.hd != nullptr) {
+    // Harmonic.get_controls fused into the staging pass (synths.py:110-117):
+    // exp_sigmoid, frame-rate Nyquist mask on float32 f0*k, row normalisation
+    // with safe_divide.  One warp per frame row, rows stay in shared memory.
+    const bool nyq = p.ctl_flags & DDSP_B200_CTL_NYQUIST;
+    for (int r = warp; r < rows_in; r += kFastThreads / 32) {
+      float* row = sX + r * Kp;
+      const float f = sF0[r];
+      float sum = 0.f;
+      for (int c = lane; c < K; c += 32) {
+        float v = row[c];
+        if (raw_scale) v = exp_sigmoid_f(v);
+        if (nyq && __fmul_rn(f, (float)(c + 1)) >= p.nyquist) v = 0.f;
+        row[c] = v;
+        sum += v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.0f / ((sum == 0.0f) ? 1e-7f : sum);
+      for (int c = lane; c < K; c += 32) row[c] *= inv;
+    }
+    __syncthreads();
+  }
   if (rows_in < nfr + 1) {                    // frame F := frame F-1
     for (int c = tid; c < Kp; c += kFastThreads)
       sX[nfr * Kp + c] = sX[(nfr - 1) * Kp + c];

@@ -30,6 +30,8 @@ struct NoiseFusedParams {
   float* audio;                     // [B,N]
   uint64_t seed, offset;
   int B, F, nb, N, frame, start, accumulate;
+  int raw;                          // mags are raw network outputs:
+  float bias;                       //   exp_sigmoid(x + bias) while staging
   int TFo, Hb, Ha;                  // output frames per tile, halo before/after
   int tiles_per_item, n_tiles;
   int mS, hS, xS, yS;               // smem row strides (floats)
@@ -104,7 +106,12 @@ noise_fused_kernel(NoiseFusedParams p) {
     for (int e = tid; e < NJ * nb; e += kNfThreads) {
       const int jl = e / nb, k = e - jl * nb;
       const int j = j0 + jl;
-      sM[jl * p.mS + k] = (j >= 0 && j < p.F) ? magb[(size_t)j * nb + k] : 0.f;
+      float m = 0.f;
+      if (j >= 0 && j < p.F) {
+        m = magb[(size_t)j * nb + k];
+        if (p.raw) m = exp_sigmoid_f(m + p.bias);   // synths.py:176-177
+      }
+      sM[jl * p.mS + k] = m;
     }
     {
       const long long p_lo = (long long)j0 * frame;
@@ -273,7 +280,8 @@ inline bool noise_fused_supported(int F, int nb, int N, int window_size) {
 inline int launch_noise_fused(const float* mags, const float* noise,
                               uint64_t seed, uint64_t offset, float* audio,
                               int B, int F, int nb, int N, int window_size,
-                              int accumulate, cudaStream_t st) {
+                              int accumulate, cudaStream_t st, int raw = 0,
+                              float bias = 0.f) {
   NoiseFusedParams p;
   if (!nf_configure(p, F, nb, N, window_size)) {
     set_error("filtered_noise_forward: shape outside the fused path");
@@ -281,6 +289,7 @@ inline int launch_noise_fused(const float* mags, const float* noise,
   }
   p.mags = mags; p.noise = noise; p.audio = audio;
   p.seed = seed; p.offset = offset; p.B = B; p.accumulate = accumulate;
+  p.raw = raw; p.bias = bias;
   const long long n_tiles = (long long)B * p.tiles_per_item;
   if (n_tiles >= (1ll << 31)) {
     set_error("filtered_noise_forward: too many tiles");

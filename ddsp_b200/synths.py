@@ -81,6 +81,12 @@ class FilteredNoise(processors.Processor):
     self.initial_bias = initial_bias
     self.seed = seed
     self._calls = itertools.count()
+    # Test hook: a [B, n_samples] tensor used instead of the Philox stream.
+    self.injected_noise = None
+
+  def next_offset(self):
+    """Per-call Philox counter offset, so successive calls draw fresh noise."""
+    return next(self._calls)
 
   def get_controls(self, magnitudes):
     """synths.py:165-179."""
@@ -95,7 +101,9 @@ class FilteredNoise(processors.Processor):
 
   def get_signal(self, magnitudes, noise=None, out=None, accumulate=False):
     """synths.py:181-196."""
+    if noise is None:
+      noise = self.injected_noise
     return core.filtered_noise(
         magnitudes, self.n_samples, window_size=self.window_size, noise=noise,
-        seed=self.seed, offset=next(self._calls), out=out,
+        seed=self.seed, offset=self.next_offset(), out=out,
         accumulate=accumulate)

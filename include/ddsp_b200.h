@@ -132,6 +132,23 @@ int ddsp_b200_filtered_noise_forward(const float* mags, const float* noise,
                                      void* workspace, size_t workspace_bytes,
                                      void* stream);
 
+/* The whole `ae.gin` decoder (ae.gin:47-72) from RAW network outputs in two
+ * launches: ProcessorGroup.__call__ (processors.py:121-131) for the DAG
+ * Harmonic -> FilteredNoise -> Add with scale_fn = exp_sigmoid.  Both
+ * get_controls (synths.py:94-121, 165-179) are applied while the frame tiles
+ * are staged in shared memory (controls never reach HBM), the noise kernel adds
+ * into the harmonic audio (processors.py:174-176).  harmonic_flags:
+ * DDSP_B200_CTL_SCALE | DDSP_B200_CTL_NYQUIST as in harmonic_controls.
+ * Returns DDSP_B200_E_UNSUPPORTED outside the decoder regime (hop % 64 == 0,
+ * n_frequencies <= 80); callers then use the per-processor entry points. */
+int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
+                              const float* f0_hz, const float* mags_raw,
+                              const float* noise, uint64_t seed, uint64_t offset,
+                              float* audio, int B, int F, int K, int nb, int N,
+                              float sample_rate, int amp_method,
+                              int harmonic_flags, int window_size,
+                              float initial_bias, void* stream);
+
 /* processors.Add.get_signal (processors.py:174-176). out may alias a or b. */
 int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,
                   void* stream);

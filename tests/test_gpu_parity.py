@@ -173,9 +173,7 @@ def test_decoder_processor_group_matches_oracle():
   harm = ddsp_b200.Harmonic(n_samples=N)
   noise = ddsp_b200.FilteredNoise(n_samples=N, window_size=0)
   add = ddsp_b200.Add()
-  # inject the parity noise through a subclass-free hook
-  orig = noise.get_signal
-  noise.get_signal = lambda magnitudes, **kw: orig(magnitudes, noise=inp['noise'], **kw)
+  noise.injected_noise = inp['noise']   # parity hook instead of the Philox stream
   pg = ddsp_b200.ProcessorGroup(dag=[
       (harm, ['amps', 'harmonic_distribution', 'f0_hz']),
       (noise, ['noise_magnitudes']),
@@ -189,6 +187,30 @@ def test_decoder_processor_group_matches_oracle():
                    ('out/signal', want['add']['signal'])]:
     emax, el2 = rel_err(_np(core.nested_lookup(key, outs)), ref)
     assert emax < TOL and el2 < TOL, (key, emax, el2)
-  fused = _np(pg(feats))
+  fused = _np(pg(feats))                # decoder_forward: 2 launches from raw
   emax, el2 = rel_err(fused, want['add']['signal'])
+  assert emax < TOL and el2 < TOL, (emax, el2)
+  # a non-default scale_fn takes the per-processor accumulate path
+  harm.scale_fn = lambda x: core.exp_sigmoid(x)
+  fused2 = _np(pg(feats))
+  emax, el2 = rel_err(fused2, want['add']['signal'])
+  assert emax < TOL and el2 < TOL, (emax, el2)
+
+
+@pytest.mark.parametrize('B,F,K,nb,N,nyq', [(3, 100, 100, 65, 6400, True),
+                                            (2, 33, 60, 65, 33 * 128, True),
+                                            (2, 64, 99, 33, 4096, False)])
+def test_decoder_forward_from_raw_matches_oracle(B, F, K, nb, N, nyq):
+  inp = synth_inputs(B, F, K, nb, N, seed=B + K, f0_hi=1500.0)
+  hc = oracle.harmonic_get_controls(inp['amps'], inp['harmonic_distribution'],
+                                    inp['f0_hz'], normalize_below_nyquist=nyq,
+                                    dtype=np.float64)
+  harm = oracle.harmonic_get_signal(n_samples=N, dtype=np.float64, **hc)
+  nc = oracle.noise_get_controls(inp['noise_magnitudes'], dtype=np.float64)
+  nz = oracle.noise_get_signal(nc['magnitudes'], inp['noise'], 0)
+  got = _np(core.decoder_forward(
+      inp['amps'], inp['harmonic_distribution'], inp['f0_hz'],
+      inp['noise_magnitudes'], N, normalize_below_nyquist=nyq, window_size=0,
+      noise=inp['noise']))
+  emax, el2 = rel_err(got, harm + nz)
   assert emax < TOL and el2 < TOL, (emax, el2)
