@@ -56,7 +56,8 @@ __device__ __forceinline__ float exp_sigmoid_f(float x) {
   const float kLog2e = 1.4426950408889634f;
   const float kLn10 = 2.302585092994046f;
   const float t = ex2_approx(-x * kLog2e);          // e^-x  (inf for x << 0)
-  const float l = __log2f(1.0f + t);                 // log2(1 + e^-x)
+  float l;                                           // log2(1 + e^-x), arg >= 1
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + t));
   return fmaf(2.0f, ex2_approx(-kLn10 * l), 1e-7f);
 }
 

@@ -112,43 +112,62 @@ __device__ __noinline__ float harmonic_sample_exact(const float* x0,
   return acc;
 }
 
-// Per-sample oscillator state for the packed recurrence.
-struct OscState {
-  float2 v;      // (sin((1+2j) phi), sin((2+2j) phi)) up to the (-1)^j flip
-  float2 d;      // v_j - v_{j-1}
-  float2 nalpha; // (-alpha, -alpha), alpha = 4 sin^2(Phi_eff / 2)
-  float2 e0, e1, o0, o1;  // accumulators: row x0/x1, even/odd j
-  float sigma;   // +1, or -1 if the chain angle was shifted by half a turn
+// Oscillator state for TWO samples (a, b) of the same frame, packed as f32x2
+// (x = sample a, y = sample b).  Two Reinsch chains run in lock-step: chain 1
+// holds the odd harmonics sin((1+2j) phi), chain 2 the even ones
+// sin((2+2j) phi); both have angle 2 phi, reduced to [-pi/2, pi/2] - a half-turn
+// shift flips the sign of every other step, which is why the accumulators are
+// split by step parity (e = even j, o = odd j) and recombined with sigma.
+struct Osc2 {
+  float2 v1, v2, d1, d2;   // chain values and differences
+  float2 nalpha;           // -4 sin^2(Phi_eff / 2) per sample
+  float2 sigma;            // +1, or -1 where the chain angle was shifted
+  float2 a0e1, a0e2, a0o1, a0o2;   // row x0: step parity x chain
+  float2 a1e1, a1e2, a1o1, a1o2;   // row x1
 };
 
-__device__ __forceinline__ void osc_init(OscState& st, uint32_t p32,
-                                         const float2* __restrict__ tab) {
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  return __fmul2_rn(a, b);
+}
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+
+__device__ __forceinline__ void osc2_init(Osc2& st, uint32_t pa, uint32_t pb,
+                                          const float2* __restrict__ tab) {
   // sin/cos of the fundamental phase: table (top bits) + 3rd-order correction
-  const uint32_t idx = (p32 + (1u << (31 - kSinTabBits))) >> (32 - kSinTabBits);
-  const int resid = (int)(p32 - (idx << (32 - kSinTabBits)));   // signed
-  const float eps = (float)resid * 1.4629180792671596e-9f;      // 2 pi / 2^32
-  const float2 sc = tab[idx & (kSinTab - 1)];
-  const float e2 = eps * eps;
-  // sin(a+e) = S (1 - e^2/2) + C e (1 - e^2/6);  cos(a+e) = C (1 - e^2/2) - S e (1 - e^2/6)
-  const float ce = fmaf(e2, -0.5f, 1.0f);
-  const float se = eps * fmaf(e2, -0.16666667f, 1.0f);
-  const float s1 = fmaf(sc.y, se, sc.x * ce);
-  const float c1 = fmaf(-sc.x, se, sc.y * ce);
-  const float ss = s1 * s1, cc = c1 * c1;
-  const bool flip = ss > cc;                 // cos(2 phi) < 0
-  const float alpha = 4.0f * fminf(ss, cc);
-  const float s2 = 2.0f * s1 * c1;
-  st.v = make_float2(s1, s2);
-  st.d = make_float2(flip ? 0.0f : 2.0f * s1, s2);
-  st.nalpha = make_float2(-alpha, -alpha);
-  st.sigma = flip ? -1.0f : 1.0f;
-  st.e0 = st.e1 = st.o0 = st.o1 = make_float2(0.f, 0.f);
+  const uint32_t ia = (pa + (1u << (31 - kSinTabBits))) >> (32 - kSinTabBits);
+  const uint32_t ib = (pb + (1u << (31 - kSinTabBits))) >> (32 - kSinTabBits);
+  const int ra = (int)(pa - (ia << (32 - kSinTabBits)));
+  const int rb = (int)(pb - (ib << (32 - kSinTabBits)));
+  const float2 ta = tab[ia & (kSinTab - 1)];
+  const float2 tb = tab[ib & (kSinTab - 1)];
+  const float2 eps = fmul2(make_float2((float)ra, (float)rb),
+                           bc2(1.4629180792671596e-9f));        // 2 pi / 2^32
+  const float2 S = make_float2(ta.x, tb.x), C = make_float2(ta.y, tb.y);
+  const float2 e2 = fmul2(eps, eps);
+  // sin(t+e) = S (1 - e^2/2) + C e (1 - e^2/6); cos(t+e) = C (1 - e^2/2) - S e (1 - e^2/6)
+  const float2 ce = ffma2(e2, bc2(-0.5f), bc2(1.0f));
+  const float2 se = fmul2(eps, ffma2(e2, bc2(-0.16666667f), bc2(1.0f)));
+  const float2 s1 = ffma2(C, se, fmul2(S, ce));
+  const float2 c1 = ffma2(make_float2(-S.x, -S.y), se, fmul2(C, ce));
+  const float2 ss = fmul2(s1, s1), cc = fmul2(c1, c1);
+  const bool fa = ss.x > cc.x, fb = ss.y > cc.y;               // cos(2 phi) < 0
+  const float2 s2 = fmul2(fadd2(s1, s1), c1);                  // sin(2 phi)
+  st.nalpha = fmul2(make_float2(fminf(ss.x, cc.x), fminf(ss.y, cc.y)), bc2(-4.0f));
+  st.v1 = s1;
+  st.v2 = s2;
+  st.d1 = make_float2(fa ? 0.0f : 2.0f * s1.x, fb ? 0.0f : 2.0f * s1.y);
+  st.d2 = s2;
+  st.sigma = make_float2(fa ? -1.0f : 1.0f, fb ? -1.0f : 1.0f);
+  st.a0e1 = st.a0e2 = st.a0o1 = st.a0o2 = make_float2(0.f, 0.f);
+  st.a1e1 = st.a1e2 = st.a1o1 = st.a1o2 = make_float2(0.f, 0.f);
 }
 
-// Advance the chain by one step (two harmonics).
-__device__ __forceinline__ void osc_step(OscState& st) {
-  st.d = ffma2(st.nalpha, st.v, st.d);
-  st.v = fadd2(st.v, st.d);
+// Advance both chains by one step (harmonics k, k+1 -> k+2, k+3).
+__device__ __forceinline__ void osc2_step(Osc2& st) {
+  st.d1 = ffma2(st.nalpha, st.v1, st.d1);
+  st.d2 = ffma2(st.nalpha, st.v2, st.d2);
+  st.v1 = fadd2(st.v1, st.d1);
+  st.v2 = fadd2(st.v2, st.d2);
 }
 
 template <bool WINDOW>
@@ -160,7 +179,7 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   unsigned long long* sP = (unsigned long long*)(smem_raw + L.off_P);
   unsigned long long* sA = (unsigned long long*)(smem_raw + L.off_A);
   unsigned long long* sD = (unsigned long long*)(smem_raw + L.off_D);
-  unsigned long long* sRed = (unsigned long long*)(smem_raw + L.off_red);
+  double* sRedD = (double*)(smem_raw + L.off_red);
   void* mbar = (void*)(smem_raw + L.off_mbar);
   float2* sTab = (float2*)(smem_raw + L.off_tab);
   float* sX = (float*)(smem_raw + L.off_x);
@@ -189,16 +208,17 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
     }
   }
 
-  // ---- 1. wrapping prefix of frame phase totals before this tile ----
-  unsigned long long part = 0;
-  for (int j = tid; j < i0; j += kFastThreads) {
-    double a0 = (double)f0b[j] * p.inv_sr;
-    double a1 = (double)f0b[min(j + 1, F - 1)] * p.inv_sr;
-    part += turns_to_fix64((double)hop * a0 + (a1 - a0) * (0.5 * (hop - 1)));
-  }
+  // ---- 1. phase at the start of this tile ----
+  // sum_{j<i0} [hop a_j + (a_{j+1}-a_j)(hop-1)/2] telescopes to
+  //   hop * sum_{j<i0} a_j + (hop-1)/2 * (a_{i0} - a_0),   a = f0 / sr,
+  // so the prefix is one double-precision sum of f0 (<= 2^15 turns: 2^-38 turn
+  // resolution), reduced over the CTA; every CTA recomputes it from f0 (<= 4 KB
+  // of L2-resident data) instead of a serial scan over time.
+  double part = 0.0;
+  for (int j = tid; j < i0; j += kFastThreads) part += (double)f0b[j];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if (lane == 0) sRed[warp] = part;
+  if (lane == 0) sRedD[warp] = part;
 
   // ---- 2. small tables ----
   const bool raw_scale = p.ctl_flags & DDSP_B200_CTL_SCALE;
@@ -238,8 +258,12 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   // Frame totals are scanned with wrapping 64-bit adds (exact, associative), 32
   // frames per warp pass; P_i = tile prefix + exclusive scan of the totals.
   if (warp == 0) {
-    unsigned long long P = 0;
-    for (int w = 0; w < kFastThreads / 32; ++w) P += sRed[w];
+    double fsum = 0.0;
+    for (int w = 0; w < kFastThreads / 32; ++w) fsum += sRedD[w];
+    const double a_first = (double)f0b[0] * p.inv_sr;
+    const double a_tile = (double)sF0[0] * p.inv_sr;
+    unsigned long long P = turns_to_fix64(
+        (double)hop * (fsum * p.inv_sr) + 0.5 * (hop - 1) * (a_tile - a_first));
     for (int base = 0; base < nfr; base += 32) {
       const int j = base + lane;
       unsigned long long tot = 0;
@@ -277,21 +301,33 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
     // exp_sigmoid, frame-rate Nyquist mask on float32 f0*k, row normalisation
     // with safe_divide.  One warp per frame row, rows stay in shared memory.
     const bool nyq = p.ctl_flags & DDSP_B200_CTL_NYQUIST;
+    const int K4 = Kp >> 2;                      // float4 groups per row
     for (int r = warp; r < rows_in; r += kFastThreads / 32) {
-      float* row = sX + r * Kp;
+      float4* row4 = reinterpret_cast<float4*>(sX + r * Kp);
       const float f = sF0[r];
       float sum = 0.f;
-      for (int c = lane; c < K; c += 32) {
-        float v = row[c];
-        if (raw_scale) v = exp_sigmoid_f(v);
-        if (nyq && __fmul_rn(f, (float)(c + 1)) >= p.nyquist) v = 0.f;
-        row[c] = v;
-        sum += v;
+      for (int c4 = lane; c4 < K4; c4 += 32) {
+        float4 v = row4[c4];
+        float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = 4 * c4 + u;
+          float w = e[u];
+          if (raw_scale) w = exp_sigmoid_f(w);
+          if (c >= K || (nyq && __fmul_rn(f, (float)(c + 1)) >= p.nyquist)) w = 0.f;
+          e[u] = w;
+          sum += w;
+        }
+        row4[c4] = make_float4(e[0], e[1], e[2], e[3]);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const float inv = 1.0f / ((sum == 0.0f) ? 1e-7f : sum);
-      for (int c = lane; c < K; c += 32) row[c] *= inv;
+      for (int c4 = lane; c4 < K4; c4 += 32) {
+        float4 v = row4[c4];
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        row4[c4] = v;
+      }
     }
     __syncthreads();
   }
@@ -337,51 +373,55 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
           kmin = __reduce_min_sync(0xffffffffu, min(ka, kb));
           kmax = __reduce_max_sync(0xffffffffu, max(ka, kb));
         }
-        OscState A, Bs;
-        osc_init(A, pa, sTab);
-        osc_init(Bs, pb, sTab);
+        Osc2 st;
+        osc2_init(st, pa, pb, sTab);
         const int k_main = kmin & ~3;            // harmonics 1..k_main unmasked
         int k = 0;
+#pragma unroll 2
         for (; k < k_main; k += 4) {
           const float4 X0 = *reinterpret_cast<const float4*>(x0 + k);
           const float4 X1 = *reinterpret_cast<const float4*>(x1 + k);
-          const float2 x0l = make_float2(X0.x, X0.y), x0h = make_float2(X0.z, X0.w);
-          const float2 x1l = make_float2(X1.x, X1.y), x1h = make_float2(X1.z, X1.w);
-          A.e0 = ffma2(x0l, A.v, A.e0);   A.e1 = ffma2(x1l, A.v, A.e1);
-          Bs.e0 = ffma2(x0l, Bs.v, Bs.e0); Bs.e1 = ffma2(x1l, Bs.v, Bs.e1);
-          osc_step(A); osc_step(Bs);
-          A.o0 = ffma2(x0h, A.v, A.o0);   A.o1 = ffma2(x1h, A.v, A.o1);
-          Bs.o0 = ffma2(x0h, Bs.v, Bs.o0); Bs.o1 = ffma2(x1h, Bs.v, Bs.o1);
-          osc_step(A); osc_step(Bs);
+          st.a0e1 = ffma2(bc2(X0.x), st.v1, st.a0e1);
+          st.a0e2 = ffma2(bc2(X0.y), st.v2, st.a0e2);
+          st.a1e1 = ffma2(bc2(X1.x), st.v1, st.a1e1);
+          st.a1e2 = ffma2(bc2(X1.y), st.v2, st.a1e2);
+          osc2_step(st);
+          st.a0o1 = ffma2(bc2(X0.z), st.v1, st.a0o1);
+          st.a0o2 = ffma2(bc2(X0.w), st.v2, st.a0o2);
+          st.a1o1 = ffma2(bc2(X1.z), st.v1, st.a1o1);
+          st.a1o2 = ffma2(bc2(X1.w), st.v2, st.a1o2);
+          osc2_step(st);
         }
         for (; k < kmax; k += 4) {               // masked tail (<= 2 passes)
           const float4 X0 = *reinterpret_cast<const float4*>(x0 + k);
           const float4 X1 = *reinterpret_cast<const float4*>(x1 + k);
-          // harmonic numbers k+1 .. k+4; live iff number <= ka / kb
-          const float2 mal = make_float2(k + 1 <= ka ? 1.f : 0.f, k + 2 <= ka ? 1.f : 0.f);
-          const float2 mah = make_float2(k + 3 <= ka ? 1.f : 0.f, k + 4 <= ka ? 1.f : 0.f);
-          const float2 mbl = make_float2(k + 1 <= kb ? 1.f : 0.f, k + 2 <= kb ? 1.f : 0.f);
-          const float2 mbh = make_float2(k + 3 <= kb ? 1.f : 0.f, k + 4 <= kb ? 1.f : 0.f);
-          const float2 x0l = make_float2(X0.x, X0.y), x0h = make_float2(X0.z, X0.w);
-          const float2 x1l = make_float2(X1.x, X1.y), x1h = make_float2(X1.z, X1.w);
-          float2 va = make_float2(A.v.x * mal.x, A.v.y * mal.y);
-          float2 vb = make_float2(Bs.v.x * mbl.x, Bs.v.y * mbl.y);
-          A.e0 = ffma2(x0l, va, A.e0);   A.e1 = ffma2(x1l, va, A.e1);
-          Bs.e0 = ffma2(x0l, vb, Bs.e0); Bs.e1 = ffma2(x1l, vb, Bs.e1);
-          osc_step(A); osc_step(Bs);
-          va = make_float2(A.v.x * mah.x, A.v.y * mah.y);
-          vb = make_float2(Bs.v.x * mbh.x, Bs.v.y * mbh.y);
-          A.o0 = ffma2(x0h, va, A.o0);   A.o1 = ffma2(x1h, va, A.o1);
-          Bs.o0 = ffma2(x0h, vb, Bs.o0); Bs.o1 = ffma2(x1h, vb, Bs.o1);
-          osc_step(A); osc_step(Bs);
+          // harmonic numbers k+1 .. k+4; live iff number <= ka (sample a) / kb
+          const float2 m1 = make_float2(k + 1 <= ka ? 1.f : 0.f, k + 1 <= kb ? 1.f : 0.f);
+          const float2 m2 = make_float2(k + 2 <= ka ? 1.f : 0.f, k + 2 <= kb ? 1.f : 0.f);
+          const float2 m3 = make_float2(k + 3 <= ka ? 1.f : 0.f, k + 3 <= kb ? 1.f : 0.f);
+          const float2 m4 = make_float2(k + 4 <= ka ? 1.f : 0.f, k + 4 <= kb ? 1.f : 0.f);
+          float2 u1 = fmul2(st.v1, m1), u2 = fmul2(st.v2, m2);
+          st.a0e1 = ffma2(bc2(X0.x), u1, st.a0e1);
+          st.a0e2 = ffma2(bc2(X0.y), u2, st.a0e2);
+          st.a1e1 = ffma2(bc2(X1.x), u1, st.a1e1);
+          st.a1e2 = ffma2(bc2(X1.y), u2, st.a1e2);
+          osc2_step(st);
+          u1 = fmul2(st.v1, m3); u2 = fmul2(st.v2, m4);
+          st.a0o1 = ffma2(bc2(X0.z), u1, st.a0o1);
+          st.a0o2 = ffma2(bc2(X0.w), u2, st.a0o2);
+          st.a1o1 = ffma2(bc2(X1.z), u1, st.a1o1);
+          st.a1o2 = ffma2(bc2(X1.w), u2, st.a1o2);
+          osc2_step(st);
         }
         {
-          const float r0a = (A.e0.x + A.e0.y) + A.sigma * (A.o0.x + A.o0.y);
-          const float r1a = (A.e1.x + A.e1.y) + A.sigma * (A.o1.x + A.o1.y);
-          ya = r0a * w0a + r1a * w1a;
-          const float r0b = (Bs.e0.x + Bs.e0.y) + Bs.sigma * (Bs.o0.x + Bs.o0.y);
-          const float r1b = (Bs.e1.x + Bs.e1.y) + Bs.sigma * (Bs.o1.x + Bs.o1.y);
-          yb = r0b * w0b + r1b * w1b;
+          const float2 r0s = ffma2(st.sigma, fadd2(st.a0o1, st.a0o2),
+                                   fadd2(st.a0e1, st.a0e2));
+          const float2 r1s = ffma2(st.sigma, fadd2(st.a1o1, st.a1o2),
+                                   fadd2(st.a1e1, st.a1e2));
+          const float2 y = ffma2(r1s, make_float2(w1a, w1b),
+                                 fmul2(r0s, make_float2(w0a, w0b)));
+          ya = y.x;
+          yb = y.y;
         }
       }
       float* o = outb + (size_t)li * hop + r0;

@@ -8,11 +8,25 @@
 // linear convolution) and overlap-adds:
 //     y_j[n]  = sum_i x_j[i] h_j[n - i],  n in [0, frame + S - 1)
 //     out[t]  = sum_j y_j[t + start - j * frame]
-// Mapping: one LANE owns one input frame j (x_j and h_j are private rows in
-// shared memory, odd strides -> no bank conflicts), one WARP owns a block of 16
-// outputs n.  The inner loop slides a 16-tap register window over h_j: per
-// input sample 1 LDS (x) + 1 LDS (new tap) feed 16 FFMAs.  A persistent grid
-// (one resident wave) amortises the cosine table over many tiles.
+//
+// Mapping.  A persistent CTA (12 warps) walks tiles of 32 input frames (29
+// output frames + 3 halo for the decoder shape); ONE LANE OWNS ONE INPUT FRAME,
+// so x_j, M_j, h_j are lane-private rows of shared memory with odd strides (no
+// bank conflicts) and every warp-wide operand of the inner loops is either
+// lane-private or a broadcast.
+//   A. stage magnitudes (exp_sigmoid fused when they are raw network outputs)
+//   B. warps 0..5: impulse-response synthesis as two half-size cosine sums
+//        h0[n]      = E[n] + O[n],  h0[S0/2 - n] = E[n] - O[n],  n = 0..S0/4
+//        E = even-k terms, O = odd-k terms of the irfft of a real spectrum
+//      (half the MACs of a full cosine sum, a quarter of an irfft's outputs);
+//      16 outputs per thread, table rows arrive as broadcast LDS.128;
+//      warps 6..11 meanwhile generate the noise (Philox4x32-10) or copy it in
+//      (the taps h_j[tap] = window[tap] * h0[|tap - shift|] are written by the
+//      same warps straight from registers)
+//   D. FIR: warp = block of 16 outputs of y_j, a 16-tap register window slides
+//      over the lane's IR row: per input sample 2 LDS feed 16 FFMA
+//   E. overlap-add in shared memory (skewed layout, blocks that could collide
+//      are serialised by frame-group), F. crop + (+= harmonic) + coalesced store
 #pragma once
 #include "noise.cuh"
 
@@ -22,7 +36,7 @@ constexpr int kNfThreads = 384;          // 12 warps
 constexpr int kNfWarps = kNfThreads / 32;
 constexpr int kNfR = 16;                 // outputs per thread in the FIR
 constexpr int kNfPad = 32;               // zero taps either side of h rows
-constexpr int kNfMaxNb = 80;             // cos table [nb][nb] must fit
+constexpr int kNfMaxNb = 129;            // table / row sizes stay in smem
 
 struct NoiseFusedParams {
   const float* __restrict__ mags;   // [B,F,nb]
@@ -34,212 +48,328 @@ struct NoiseFusedParams {
   float bias;                       //   exp_sigmoid(x + bias) while staging
   int TFo, Hb, Ha;                  // output frames per tile, halo before/after
   int tiles_per_item, n_tiles;
-  int mS, hS, xS, yS;               // smem row strides (floats)
-  int ylen;                         // frame + S - 1
+  int Q, QP, ne, no;                // S0/4, padded column count, #even k, #odd k
+  int mS, hS, xS;                   // smem row strides (floats)
+  int ylen, nblk, ngrp;             // frame + S - 1, FIR blocks, frame groups
+  int outLen;                       // skewed OLA buffer length
   IrGeom g;
 };
 
 struct NfSmem {
-  size_t off_cos, off_win, off_m, off_h, off_x, off_y, total;
+  size_t off_te, off_to, off_win, off_m, off_raw, off_h, off_x, off_out, total;
 };
 
 __host__ __device__ inline NfSmem nf_smem_layout(const NoiseFusedParams& p) {
   NfSmem s;
   size_t o = 0;
-  const int nhp = (p.g.S0 / 2 + 1 + 3) & ~3;        // |n| values, padded to 4
-  s.off_cos = o; o += sizeof(float) * (size_t)p.nb * nhp;  // [k][n]
-  s.off_win = o; o += sizeof(float) * (size_t)p.g.S;
+  s.off_te = o;  o += sizeof(float) * (size_t)p.ne * p.QP;
+  s.off_to = o;  o += sizeof(float) * (size_t)p.no * p.QP;
+  s.off_win = o; o += sizeof(float) * (size_t)((p.g.S + 3) & ~3);
   s.off_m = o;   o += sizeof(float) * 32 * (size_t)p.mS;
+  s.off_raw = o; o += sizeof(float) * 32 * (size_t)p.nb;
   s.off_h = o;   o += sizeof(float) * 32 * (size_t)p.hS;
   s.off_x = o;   o += sizeof(float) * 32 * (size_t)p.xS;
-  // y aliases the cos/m region?  kept separate in v1 for clarity.
-  s.off_y = o;   o += sizeof(float) * 32 * (size_t)p.yS;
+  s.off_out = o; o += sizeof(float) * (size_t)p.outLen;
   s.total = (o + 15) & ~(size_t)15;
   return s;
+}
+
+// cp.async (LDGSTS) of one float: global -> shared without register staging.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// One block of W = 4*W4 columns n0..n0+W-1 of BOTH half-size cosine sums
+//   E[n] = sum_k' m[2k']   cos(2 pi 2k' n / S0),  O[n] = sum_k' m[2k'+1] cos(...)
+// followed by the tap epilogue: h0[n] = E + O at zero-phase offsets +-n and
+// h0[S0/2 - n] = E - O at offsets +-(S0/2 - n); h[tap] = win[tap] * h0[|tap-shift|].
+template <int W4>
+__device__ __forceinline__ void ir_block_eo(const float* __restrict__ mrow,
+                                            const float* __restrict__ tE,
+                                            const float* __restrict__ tO, int QP,
+                                            int ne, int no, int n0, int Q,
+                                            int shift, int S,
+                                            const float* __restrict__ win,
+                                            float* __restrict__ hrow) {
+  float aE[4 * W4], aO[4 * W4];
+#pragma unroll
+  for (int c = 0; c < 4 * W4; ++c) aE[c] = aO[c] = 0.f;
+#pragma unroll 3
+  for (int k = 0; k < ne; ++k) {
+    const float m = mrow[2 * k];
+    const float4* t4 = reinterpret_cast<const float4*>(tE + k * QP + n0);
+#pragma unroll
+    for (int q = 0; q < W4; ++q) {
+      const float4 c = t4[q];
+      aE[4 * q + 0] = fmaf(m, c.x, aE[4 * q + 0]);
+      aE[4 * q + 1] = fmaf(m, c.y, aE[4 * q + 1]);
+      aE[4 * q + 2] = fmaf(m, c.z, aE[4 * q + 2]);
+      aE[4 * q + 3] = fmaf(m, c.w, aE[4 * q + 3]);
+    }
+  }
+#pragma unroll 3
+  for (int k = 0; k < no; ++k) {
+    const float m = mrow[2 * k + 1];
+    const float4* t4 = reinterpret_cast<const float4*>(tO + k * QP + n0);
+#pragma unroll
+    for (int q = 0; q < W4; ++q) {
+      const float4 c = t4[q];
+      aO[4 * q + 0] = fmaf(m, c.x, aO[4 * q + 0]);
+      aO[4 * q + 1] = fmaf(m, c.y, aO[4 * q + 1]);
+      aO[4 * q + 2] = fmaf(m, c.z, aO[4 * q + 2]);
+      aO[4 * q + 3] = fmaf(m, c.w, aO[4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4 * W4; ++c) {
+    const int n = n0 + c;
+    if (n > Q) continue;
+    const float hp = aE[c] + aO[c];       // h0 at |offset| = n
+    const float hm = aE[c] - aO[c];       // h0 at |offset| = 2Q - n
+    const int n2 = 2 * Q - n;
+    int t;
+    t = shift + n;  if (t >= 0 && t < S) hrow[t] = win[t] * hp;
+    t = shift - n;  if (n != 0 && t >= 0 && t < S) hrow[t] = win[t] * hp;
+    if (n2 != n) {
+      t = shift + n2; if (t >= 0 && t < S) hrow[t] = win[t] * hm;
+      t = shift - n2; if (t >= 0 && t < S) hrow[t] = win[t] * hm;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kNfThreads, 2)
 noise_fused_kernel(NoiseFusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const NfSmem L = nf_smem_layout(p);
-  float* sCos = (float*)(smem_raw + L.off_cos);
+  float* sTE = (float*)(smem_raw + L.off_te);
+  float* sTO = (float*)(smem_raw + L.off_to);
   float* sWin = (float*)(smem_raw + L.off_win);
   float* sM = (float*)(smem_raw + L.off_m);
+  float* sRaw = (float*)(smem_raw + L.off_raw);
   float* sH = (float*)(smem_raw + L.off_h);
   float* sX = (float*)(smem_raw + L.off_x);
-  float* sY = (float*)(smem_raw + L.off_y);
+  float* sOut = (float*)(smem_raw + L.off_out);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const IrGeom g = p.g;
   const int nb = p.nb, S = g.S, S0 = g.S0, frame = p.frame;
-  const int nh = S0 / 2 + 1;
-  const int nhp = (nh + 3) & ~3;
+  const int Q = p.Q, QP = p.QP, ne = p.ne, no = p.no;
+  const float invS0 = 1.0f / (float)S0;
 
-  // ---- once per CTA: cos table [k][n] (coefficient c_k / S0 folded in) and
-  //      the causal window ----
+  // ---- once per CTA: cosine tables, window, zero pads ----
   {
-    const float inv = 1.0f / (float)S0;
-    for (int e = tid; e < nb * nhp; e += kNfThreads) {
-      const int k = e / nhp, n = e - k * nhp;
-      const int ph = (int)(((long long)k * n) % S0);
-      const float c = (k == 0 || k == nb - 1) ? inv : 2.0f * inv;
-      sCos[e] = (n < nh) ? c * cospif(2.0f * (float)ph / (float)S0) : 0.f;
+    for (int e = tid; e < ne * QP; e += kNfThreads) {
+      const int k = e / QP, n = e - k * QP;          // even harmonic 2k
+      const int ph = (int)(((long long)2 * k * n) % S0);
+      sTE[e] = (n <= Q) ? cospif(2.0f * (float)ph * invS0) : 0.f;
+    }
+    for (int e = tid; e < no * QP; e += kNfThreads) {
+      const int k = e / QP, n = e - k * QP;          // odd harmonic 2k+1
+      const int ph = (int)(((long long)(2 * k + 1) * n) % S0);
+      sTO[e] = (n < Q) ? cospif(2.0f * (float)ph * invS0) : 0.f;
     }
     for (int j = tid; j < S; j += kNfThreads) {
       int idx; float w;
       ir_tap(g, j, &idx, &w);
       sWin[j] = w;
     }
-    // zero the h pads once (taps are rewritten every tile, pads never)
     for (int e = tid; e < 32 * p.hS; e += kNfThreads) sH[e] = 0.f;
     for (int e = tid; e < 32 * p.xS; e += kNfThreads) sX[e] = 0.f;
   }
   __syncthreads();
 
-  const int NJ = p.TFo + p.Hb + p.Ha;            // input frames per tile (<= 32)
+  const int nblk8 = (Q + 1 + 7) >> 3;                // 8-column blocks of E/O
+  const int nq = frame >> 2;                         // noise quads per frame
+  const int n_ir_warps = min(nblk8, kNfWarps - 4);
+
+  // raw magnitudes of a tile -> sRaw, asynchronously (consumed one tile later)
+  auto prefetch_mags = [&](int tile) {
+    const int b = tile / p.tiles_per_item;
+    const int j0 = (tile - b * p.tiles_per_item) * p.TFo - p.Hb;
+    const float* magb = p.mags + (size_t)b * p.F * nb;
+    for (int e = tid; e < 32 * nb; e += kNfThreads) {
+      const int jl = e / nb;
+      const int j = j0 + jl;
+      if (j >= 0 && j < p.F) cp_async4(sRaw + e, magb + ((long long)j0 * nb + e));
+    }
+  };
+  if (blockIdx.x < p.n_tiles) prefetch_mags(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int b = tile / p.tiles_per_item;
     const int q0 = (tile - b * p.tiles_per_item) * p.TFo;   // first output frame
     const int j0 = q0 - p.Hb;                                // first input frame
-    const float* magb = p.mags + (size_t)b * p.F * nb;
 
-    // ---- 1. stage magnitudes and noise for input frames j0 .. j0+NJ-1 ----
-    for (int e = tid; e < NJ * nb; e += kNfThreads) {
-      const int jl = e / nb, k = e - jl * nb;
+    // ---- A. magnitudes: exp_sigmoid (if raw) and c_k / S0 while moving the
+    //         prefetched slab into lane-private rows ----
+    cp_async_wait_all();
+    __syncthreads();
+    for (int jl = warp; jl < 32; jl += kNfWarps) {
       const int j = j0 + jl;
-      float m = 0.f;
-      if (j >= 0 && j < p.F) {
-        m = magb[(size_t)j * nb + k];
-        if (p.raw) m = exp_sigmoid_f(m + p.bias);   // synths.py:176-177
+      const bool live = (j >= 0 && j < p.F);
+      const float* src = sRaw + jl * nb;
+      float* dst = sM + jl * p.mS;
+      for (int k = lane; k < nb; k += 32) {
+        float m = 0.f;
+        if (live) {
+          m = src[k];
+          if (p.raw) m = exp_sigmoid_f(m + p.bias);           // synths.py:176-177
+          m *= (k == 0 || k == nb - 1) ? invS0 : 2.0f * invS0;
+        }
+        dst[k] = m;
       }
-      sM[jl * p.mS + k] = m;
     }
-    {
-      const long long p_lo = (long long)j0 * frame;
-      const long long p_hi = (long long)(j0 + NJ) * frame;   // exclusive
-      const long long q_lo = (p_lo >= 0 ? p_lo : 0) >> 2;
-      const long long q_hi = ((p_hi < p.N ? p_hi : p.N) + 3) >> 2;
-      // zero everything first when the tile touches the signal edges
-      if (p_lo < 0 || p_hi > p.N) {
-        for (int e = tid; e < NJ * p.xS; e += kNfThreads) sX[e] = 0.f;
-        __syncthreads();
+    for (int e = tid; e < p.outLen; e += kNfThreads) sOut[e] = 0.f;
+    __syncthreads();
+    {   // the staging buffer is free again: fetch the next tile's magnitudes
+      const int nxt = tile + gridDim.x;
+      if (nxt < p.n_tiles) prefetch_mags(nxt);
+    }
+
+    // ---- B. IR synthesis + taps (warps 0..) || noise staging (other warps) ----
+    if (warp < n_ir_warps) {
+      for (int blk = warp; blk < nblk8; blk += n_ir_warps) {
+        const int n0 = blk << 3;
+        const float* mrow = sM + lane * p.mS;
+        float* hrow = sH + lane * p.hS + kNfPad;
+        if (Q + 1 - n0 > 4)
+          ir_block_eo<2>(mrow, sTE, sTO, QP, ne, no, n0, Q, g.shift, S, sWin, hrow);
+        else
+          ir_block_eo<1>(mrow, sTE, sTO, QP, ne, no, n0, Q, g.shift, S, sWin, hrow);
       }
+    } else {
+      const int nw = kNfWarps - n_ir_warps;
       const float* nzb = p.noise ? p.noise + (size_t)b * p.N : nullptr;
-      for (long long q = q_lo + tid; q < q_hi; q += kNfThreads) {
-        float v[4];
-        if (nzb) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const long long pp = 4 * q + u;
-            v[u] = pp < p.N ? nzb[pp] : 0.f;
+      const int total = 32 * nq;                    // quads in the tile
+      for (int e = (warp - n_ir_warps) * 32 + lane; e < total; e += nw * 32) {
+        const int jl = e / nq, qd = e - jl * nq;
+        const long long pp = (long long)(j0 + jl) * frame + 4 * qd;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        if (pp >= 0 && pp < p.N) {
+          if (nzb) {
+            v0 = nzb[pp];
+            if (pp + 1 < p.N) v1 = nzb[pp + 1];
+            if (pp + 2 < p.N) v2 = nzb[pp + 2];
+            if (pp + 3 < p.N) v3 = nzb[pp + 3];
+          } else {
+            const float4 r = noise4((uint32_t)(pp >> 2), (uint32_t)b, p.seed,
+                                    p.offset);
+            v0 = r.x;
+            if (pp + 1 < p.N) v1 = r.y;
+            if (pp + 2 < p.N) v2 = r.z;
+            if (pp + 3 < p.N) v3 = r.w;
           }
-        } else {
-          const float4 r = noise4((uint32_t)q, (uint32_t)b, p.seed, p.offset);
-          v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const long long pp = 4 * q + u;
-          if (pp >= p_lo && pp < p_hi && pp < p.N) {
-            const int rel = (int)(pp - p_lo);
-            const int jl = rel / frame, i = rel - jl * frame;
-            sX[jl * p.xS + i] = v[u];
-          }
-        }
+        float* d = sX + jl * p.xS + 4 * qd;
+        d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
       }
     }
     __syncthreads();
 
-    // ---- 2. impulse responses: lane = frame, warp = block of 8 |n| values ----
-    //   h0[n] = sum_k (c_k/S0) M_k cos(2 pi k n / S0), n = 0 .. S0/2
-    //   tap j <-> zero-phase offset nz = j - shift; h[j] = win[j] * h0[|nz|]
-    for (int n0 = warp * 8; n0 < nh; n0 += kNfWarps * 8) {
-      float acc[8];
+    // The += operand (harmonic audio) is fetched now so its latency hides
+    // behind the FIR; phase F consumes it.
+    float* outb = p.audio + (size_t)b * p.N;
+    const int nq_out = p.TFo * nq;
+    const bool use_pre = p.accumulate && nq_out <= 2 * kNfThreads;
+    float4 pre[2];
+    pre[0] = pre[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (use_pre) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-      const float* mrow = sM + lane * p.mS;
-      if (n0 + 4 < nhp) {
-#pragma unroll 5
-        for (int k = 0; k < nb; ++k) {
-          const float m = mrow[k];
-          const float4 ca = *reinterpret_cast<const float4*>(sCos + k * nhp + n0);
-          const float4 cb = *reinterpret_cast<const float4*>(sCos + k * nhp + n0 + 4);
-          acc[0] = fmaf(m, ca.x, acc[0]); acc[1] = fmaf(m, ca.y, acc[1]);
-          acc[2] = fmaf(m, ca.z, acc[2]); acc[3] = fmaf(m, ca.w, acc[3]);
-          acc[4] = fmaf(m, cb.x, acc[4]); acc[5] = fmaf(m, cb.y, acc[5]);
-          acc[6] = fmaf(m, cb.z, acc[6]); acc[7] = fmaf(m, cb.w, acc[7]);
-        }
-      } else {
-        for (int k = 0; k < nb; ++k) {
-          const float m = mrow[k];
-          const float4 ca = *reinterpret_cast<const float4*>(sCos + k * nhp + n0);
-          acc[0] = fmaf(m, ca.x, acc[0]); acc[1] = fmaf(m, ca.y, acc[1]);
-          acc[2] = fmaf(m, ca.z, acc[2]); acc[3] = fmaf(m, ca.w, acc[3]);
-        }
-      }
-      float* hrow = sH + lane * p.hS + kNfPad;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int n = n0 + c;
-        if (n < nh) {
-          // taps whose |zero-phase offset| (mod S0) equals n
-          const int ja = g.shift + n, jb = g.shift - n;
-          if (ja < S) hrow[ja] = sWin[ja] * acc[c];
-          if (jb >= 0 && jb < S && jb != ja) hrow[jb] = sWin[jb] * acc[c];
+      for (int it = 0; it < 2; ++it) {
+        const int e = tid + it * kNfThreads;
+        if (e < nq_out) {
+          const int ql = e / nq, qd = e - ql * nq;
+          const int t = (q0 + ql) * frame + 4 * qd;
+          if (q0 + ql < p.F && t + 3 < p.N &&
+              (reinterpret_cast<uintptr_t>(outb + t) & 15) == 0)
+            pre[it] = *reinterpret_cast<const float4*>(outb + t);
         }
       }
     }
-    __syncthreads();
 
-    // ---- 3. FIR: lane = frame j, warp = 16-output block of y_j ----
+    // ---- D. FIR (lane = frame, warp = 16-output block), E. overlap-add ----
     {
       const float* xrow = sX + lane * p.xS;
       const float* hrow = sH + lane * p.hS + kNfPad;
-      float* yrow = sY + lane * p.yS;
-      const int nblk = (p.ylen + kNfR - 1) / kNfR;
       const int nchunk = (frame + 15) >> 4;
-      for (int blk = warp; blk < nblk; blk += kNfWarps) {
+      for (int round = 0; round * kNfWarps < p.nblk; ++round) {
+        const int blk = round * kNfWarps + warp;
         const int n0 = blk * kNfR;
         float acc[kNfR];
 #pragma unroll
         for (int c = 0; c < kNfR; ++c) acc[c] = 0.f;
-        const int i_lo = max(0, n0 - (S - 1));
-        const int i_hi = min(frame - 1, n0 + kNfR - 1);
-        for (int ch = i_lo >> 4; ch <= (i_hi >> 4) && ch < nchunk; ++ch) {
-          const int ib = ch << 4;
-          float W[kNfR];
+        if (blk < p.nblk) {
+          const int i_lo = max(0, n0 - (S - 1));
+          const int i_hi = min(frame - 1, n0 + kNfR - 1);
+          for (int ch = i_lo >> 4; ch <= (i_hi >> 4) && ch < nchunk; ++ch) {
+            const int ib = ch << 4;
+            float W[kNfR];
 #pragma unroll
-          for (int r = 0; r < kNfR; ++r) W[r] = hrow[n0 + r - ib];
+            for (int r = 0; r < kNfR; ++r) W[r] = hrow[n0 + r - ib];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const float xv = xrow[ib + u];
+            for (int u = 0; u < 16; ++u) {
+              const float xv = xrow[ib + u];
 #pragma unroll
-            for (int c = 0; c < kNfR; ++c)
-              acc[c] = fmaf(xv, W[(c - u) & 15], acc[c]);
-            W[(-u - 1) & 15] = hrow[n0 - (ib + u + 1)];
+              for (int c = 0; c < kNfR; ++c)
+                acc[c] = fmaf(xv, W[(c - u) & 15], acc[c]);
+              W[(-u - 1) & 15] = hrow[n0 - (ib + u + 1)];
+            }
           }
         }
+        // overlap-add: position o = frame * lane + n, stored skewed by o / frame
+        // so lanes hit distinct banks.  Blocks of one frame-group cannot collide.
+        const int grp = n0 / frame;
+        const int nin = n0 - grp * frame;            // offset inside the group
+        float* orow = sOut + (frame + 1) * (lane + grp) + nin;
+        for (int gph = 0; gph < p.ngrp; ++gph) {
+          if (blk < p.nblk && grp == gph) {
 #pragma unroll
-        for (int c = 0; c < kNfR; ++c) yrow[n0 + c] = acc[c];
+            for (int c = 0; c < kNfR; ++c) orow[c] += acc[c];
+          }
+          __syncthreads();
+        }
       }
     }
-    __syncthreads();
 
-    // ---- 4. overlap-add + crop + (accumulate) + store ----
+    // ---- F. crop, (+= harmonic), store: 4 consecutive samples per thread ----
     {
-      const int t_lo = q0 * frame;
-      const int t_hi = min((q0 + p.TFo) * frame, p.N);
-      float* outb = p.audio + (size_t)b * p.N;
-      for (int t = t_lo + tid; t < t_hi; t += kNfThreads) {
-        const int q = t + p.start;                 // index into the OLA buffer
-        int j_hi = q / frame;                      // last frame that can reach q
-        int j_lo = (q - (p.ylen - 1) + frame - 1) / frame;
-        if (q - (p.ylen - 1) < 0) j_lo = 0;
-        j_hi = min(j_hi, p.F - 1);
-        float acc = 0.f;
-        for (int j = j_lo; j <= j_hi; ++j)
-          acc += sY[(j - j0) * p.yS + (q - j * frame)];
-        if (p.accumulate) acc += outb[t];
-        outb[t] = acc;
+      int it = 0;
+      for (int e = tid; e < nq_out; e += kNfThreads, ++it) {
+        const int ql = e / nq, qd = e - ql * nq;
+        const int t = (q0 + ql) * frame + 4 * qd;
+        if (t >= p.N || q0 + ql >= p.F) continue;
+        const int r0 = 4 * qd + p.start;
+        const int f0 = r0 / frame;
+        const int rem = r0 - f0 * frame;
+        const int o = (ql + p.Hb) * frame + r0;     // unskewed OLA position
+        const int sk = ql + p.Hb + f0;               // skew = position / frame
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = sOut[o + u + sk + ((rem + u >= frame) ? 1 : 0)];
+        if (t + 3 < p.N && ((reinterpret_cast<uintptr_t>(outb + t) & 15) == 0)) {
+          float4* dst = reinterpret_cast<float4*>(outb + t);
+          float4 r = make_float4(v[0], v[1], v[2], v[3]);
+          if (p.accumulate) {
+            const float4 a = use_pre ? (it == 0 ? pre[0] : pre[1]) : *dst;
+            r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+          }
+          *dst = r;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (t + u < p.N) {
+              float r = v[u];
+              if (p.accumulate) r += outb[t + u];
+              outb[t + u] = r;
+            }
+          }
+        }
       }
     }
     __syncthreads();
@@ -251,24 +381,30 @@ inline int nf_odd(int v) { return v | 1; }
 // Fills the derived fields; returns false if the shape is outside the fused path.
 inline bool nf_configure(NoiseFusedParams& p, int F, int nb, int N,
                          int window_size) {
-  if (nb < 2 || nb > kNfMaxNb) return false;
+  if (nb < 3 || nb > kNfMaxNb || (nb & 1) == 0) return false;   // S0 % 4 == 0
   p.g = make_ir_geom(nb, window_size);
   p.F = F; p.nb = nb; p.N = N;
   p.frame = (N + F - 1) / F;
   const int S = p.g.S;
   p.start = (S - 1) / 2 - 1;
   if (p.start < 0) return false;
-  if (p.frame < 8 || p.frame > 1024) return false;
+  if (p.frame < 16 || p.frame > 1024 || (p.frame & 15)) return false;
   p.ylen = p.frame + S - 1;
   p.Hb = (S - 1 - p.start + p.frame - 1) / p.frame;   // ceil((S-1-start)/frame)
   p.Ha = (p.frame - 1 + p.start) / p.frame;
   p.TFo = 32 - p.Hb - p.Ha;
   if (p.TFo < 16) return false;
   p.tiles_per_item = (F + p.TFo - 1) / p.TFo;
+  p.Q = p.g.S0 / 4;
+  p.QP = (p.Q + 1 + 3) & ~3;
+  p.ne = (nb + 1) / 2;
+  p.no = (nb - 1) / 2;
   p.mS = nf_odd(nb);
   p.hS = nf_odd(S + 2 * kNfPad);
   p.xS = nf_odd(((p.frame + 15) & ~15) + 16);
-  p.yS = nf_odd(((p.ylen + kNfR - 1) / kNfR) * kNfR);
+  p.nblk = (p.ylen + kNfR - 1) / kNfR;
+  p.ngrp = (p.nblk * kNfR + p.frame - 1) / p.frame;
+  p.outLen = (p.frame + 1) * (32 + p.ngrp) + 16;
   return nf_smem_layout(p).total <= 200 * 1024;
 }
 
