@@ -23,8 +23,11 @@
 //      warps 6..11 meanwhile generate the noise (Philox4x32-10) or copy it in
 //      (the taps h_j[tap] = window[tap] * h0[|tap - shift|] are written by the
 //      same warps straight from registers)
-//   D. FIR: warp = block of 16 outputs of y_j, a 16-tap register window slides
-//      over the lane's IR row: per input sample 2 LDS feed 16 FFMA
+//   D. FIR: warp = block of 16 outputs of y_j held as 8 packed f32x2
+//      accumulators; two register windows of 8 tap PAIRS slide over the lane's
+//      IR row (one window of even-aligned pairs for even input samples, one of
+//      odd-aligned pairs - from a copy of the row shifted by one tap - for odd
+//      ones), so two input samples cost 3 LDS.64 + 16 FFMA2 (= 32 lane-FMAs)
 //   E. overlap-add in shared memory (skewed layout, blocks that could collide
 //      are serialised by frame-group), F. crop + (+= harmonic) + coalesced store
 #pragma once
@@ -49,7 +52,8 @@ struct NoiseFusedParams {
   int TFo, Hb, Ha;                  // output frames per tile, halo before/after
   int tiles_per_item, n_tiles;
   int Q, QP, ne, no;                // S0/4, padded column count, #even k, #odd k
-  int mS, hS, xS;                   // smem row strides (floats)
+  int mS, hS, xS;                   // smem row strides (floats); hS, xS = 2 mod 4
+  int nq_shift;                     // log2(frame / 4) or -1
   int ylen, nblk, ngrp;             // frame + S - 1, FIR blocks, frame groups
   int outLen;                       // skewed OLA buffer length
   IrGeom g;
@@ -67,11 +71,15 @@ __host__ __device__ inline NfSmem nf_smem_layout(const NoiseFusedParams& p) {
   s.off_win = o; o += sizeof(float) * (size_t)((p.g.S + 3) & ~3);
   s.off_m = o;   o += sizeof(float) * 32 * (size_t)p.mS;
   s.off_raw = o; o += sizeof(float) * 32 * (size_t)p.nb;
-  s.off_h = o;   o += sizeof(float) * 32 * (size_t)p.hS;
+  s.off_h = o;   o += sizeof(float) * 64 * (size_t)p.hS;   // even + odd copies
   s.off_x = o;   o += sizeof(float) * 32 * (size_t)p.xS;
   s.off_out = o; o += sizeof(float) * (size_t)p.outLen;
   s.total = (o + 15) & ~(size_t)15;
   return s;
+}
+
+__device__ __forceinline__ float2 nf_ffma2(float x, float2 w, float2 acc) {
+  return __ffma2_rn(make_float2(x, x), w, acc);
 }
 
 // cp.async (LDGSTS) of one float: global -> shared without register staging.
@@ -96,7 +104,8 @@ __device__ __forceinline__ void ir_block_eo(const float* __restrict__ mrow,
                                             int ne, int no, int n0, int Q,
                                             int shift, int S,
                                             const float* __restrict__ win,
-                                            float* __restrict__ hrow) {
+                                            float* __restrict__ hrow,
+                                            float* __restrict__ hrow_odd) {
   float aE[4 * W4], aO[4 * W4];
 #pragma unroll
   for (int c = 0; c < 4 * W4; ++c) aE[c] = aO[c] = 0.f;
@@ -134,11 +143,16 @@ __device__ __forceinline__ void ir_block_eo(const float* __restrict__ mrow,
     const float hm = aE[c] - aO[c];       // h0 at |offset| = 2Q - n
     const int n2 = 2 * Q - n;
     int t;
-    t = shift + n;  if (t >= 0 && t < S) hrow[t] = win[t] * hp;
-    t = shift - n;  if (n != 0 && t >= 0 && t < S) hrow[t] = win[t] * hp;
+    float v;
+    t = shift + n;
+    if (t >= 0 && t < S) { v = win[t] * hp; hrow[t] = v; hrow_odd[t + 1] = v; }
+    t = shift - n;
+    if (n != 0 && t >= 0 && t < S) { v = win[t] * hp; hrow[t] = v; hrow_odd[t + 1] = v; }
     if (n2 != n) {
-      t = shift + n2; if (t >= 0 && t < S) hrow[t] = win[t] * hm;
-      t = shift - n2; if (t >= 0 && t < S) hrow[t] = win[t] * hm;
+      t = shift + n2;
+      if (t >= 0 && t < S) { v = win[t] * hm; hrow[t] = v; hrow_odd[t + 1] = v; }
+      t = shift - n2;
+      if (t >= 0 && t < S) { v = win[t] * hm; hrow[t] = v; hrow_odd[t + 1] = v; }
     }
   }
 }
@@ -166,19 +180,20 @@ noise_fused_kernel(NoiseFusedParams p) {
     for (int e = tid; e < ne * QP; e += kNfThreads) {
       const int k = e / QP, n = e - k * QP;          // even harmonic 2k
       const int ph = (int)(((long long)2 * k * n) % S0);
-      sTE[e] = (n <= Q) ? cospif(2.0f * (float)ph * invS0) : 0.f;
+      const float ck = (k == 0 || 2 * k == nb - 1) ? invS0 : 2.0f * invS0;
+      sTE[e] = (n <= Q) ? ck * cospif(2.0f * (float)ph * invS0) : 0.f;
     }
     for (int e = tid; e < no * QP; e += kNfThreads) {
       const int k = e / QP, n = e - k * QP;          // odd harmonic 2k+1
       const int ph = (int)(((long long)(2 * k + 1) * n) % S0);
-      sTO[e] = (n < Q) ? cospif(2.0f * (float)ph * invS0) : 0.f;
+      sTO[e] = (n < Q) ? 2.0f * invS0 * cospif(2.0f * (float)ph * invS0) : 0.f;
     }
     for (int j = tid; j < S; j += kNfThreads) {
       int idx; float w;
       ir_tap(g, j, &idx, &w);
       sWin[j] = w;
     }
-    for (int e = tid; e < 32 * p.hS; e += kNfThreads) sH[e] = 0.f;
+    for (int e = tid; e < 64 * p.hS; e += kNfThreads) sH[e] = 0.f;
     for (int e = tid; e < 32 * p.xS; e += kNfThreads) sX[e] = 0.f;
   }
   __syncthreads();
@@ -211,17 +226,17 @@ noise_fused_kernel(NoiseFusedParams p) {
     __syncthreads();
     for (int jl = warp; jl < 32; jl += kNfWarps) {
       const int j = j0 + jl;
-      const bool live = (j >= 0 && j < p.F);
       const float* src = sRaw + jl * nb;
       float* dst = sM + jl * p.mS;
-      for (int k = lane; k < nb; k += 32) {
-        float m = 0.f;
-        if (live) {
-          m = src[k];
-          if (p.raw) m = exp_sigmoid_f(m + p.bias);           // synths.py:176-177
-          m *= (k == 0 || k == nb - 1) ? invS0 : 2.0f * invS0;
-        }
-        dst[k] = m;
+      if (j < 0 || j >= p.F) {
+        for (int k = lane; k < nb; k += 32) dst[k] = 0.f;
+      } else if (p.raw) {
+#pragma unroll 3
+        for (int k = lane; k < nb; k += 32)
+          dst[k] = exp_sigmoid_f(src[k] + p.bias);             // synths.py:176-177
+      } else {
+#pragma unroll 3
+        for (int k = lane; k < nb; k += 32) dst[k] = src[k];
       }
     }
     for (int e = tid; e < p.outLen; e += kNfThreads) sOut[e] = 0.f;
@@ -237,36 +252,55 @@ noise_fused_kernel(NoiseFusedParams p) {
         const int n0 = blk << 3;
         const float* mrow = sM + lane * p.mS;
         float* hrow = sH + lane * p.hS + kNfPad;
+        float* hrow_odd = sH + (32 + lane) * p.hS + kNfPad;
         if (Q + 1 - n0 > 4)
-          ir_block_eo<2>(mrow, sTE, sTO, QP, ne, no, n0, Q, g.shift, S, sWin, hrow);
+          ir_block_eo<2>(mrow, sTE, sTO, QP, ne, no, n0, Q, g.shift, S, sWin, hrow,
+                         hrow_odd);
         else
-          ir_block_eo<1>(mrow, sTE, sTO, QP, ne, no, n0, Q, g.shift, S, sWin, hrow);
+          ir_block_eo<1>(mrow, sTE, sTO, QP, ne, no, n0, Q, g.shift, S, sWin, hrow,
+                         hrow_odd);
       }
     } else {
       const int nw = kNfWarps - n_ir_warps;
       const float* nzb = p.noise ? p.noise + (size_t)b * p.N : nullptr;
       const int total = 32 * nq;                    // quads in the tile
-      for (int e = (warp - n_ir_warps) * 32 + lane; e < total; e += nw * 32) {
-        const int jl = e / nq, qd = e - jl * nq;
-        const long long pp = (long long)(j0 + jl) * frame + 4 * qd;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-        if (pp >= 0 && pp < p.N) {
-          if (nzb) {
-            v0 = nzb[pp];
-            if (pp + 1 < p.N) v1 = nzb[pp + 1];
-            if (pp + 2 < p.N) v2 = nzb[pp + 2];
-            if (pp + 3 < p.N) v3 = nzb[pp + 3];
-          } else {
-            const float4 r = noise4((uint32_t)(pp >> 2), (uint32_t)b, p.seed,
-                                    p.offset);
-            v0 = r.x;
-            if (pp + 1 < p.N) v1 = r.y;
-            if (pp + 2 < p.N) v2 = r.z;
-            if (pp + 3 < p.N) v3 = r.w;
-          }
+      const long long p_lo = (long long)j0 * frame;
+      const bool interior = (p_lo >= 0) && (p_lo + 32ll * frame <= p.N) && !nzb;
+      if (interior) {
+        // every sample exists: no bounds checks, 32-bit index math
+        const uint32_t qbase = (uint32_t)(p_lo >> 2);
+        for (int e = (warp - n_ir_warps) * 32 + lane; e < total; e += nw * 32) {
+          int jl, qd;
+          if (p.nq_shift >= 0) { jl = e >> p.nq_shift; qd = e & (nq - 1); }
+          else { jl = e / nq; qd = e - jl * nq; }
+          const float4 r = noise4(qbase + (uint32_t)e, (uint32_t)b, p.seed, p.offset);
+          float2* d = reinterpret_cast<float2*>(sX + jl * p.xS + 4 * qd);
+          d[0] = make_float2(r.x, r.y);
+          d[1] = make_float2(r.z, r.w);
         }
-        float* d = sX + jl * p.xS + 4 * qd;
-        d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
+      } else {
+        for (int e = (warp - n_ir_warps) * 32 + lane; e < total; e += nw * 32) {
+          const int jl = e / nq, qd = e - jl * nq;
+          const long long pp = (long long)(j0 + jl) * frame + 4 * qd;
+          float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+          if (pp >= 0 && pp < p.N) {
+            if (nzb) {
+              v0 = nzb[pp];
+              if (pp + 1 < p.N) v1 = nzb[pp + 1];
+              if (pp + 2 < p.N) v2 = nzb[pp + 2];
+              if (pp + 3 < p.N) v3 = nzb[pp + 3];
+            } else {
+              const float4 r = noise4((uint32_t)(pp >> 2), (uint32_t)b, p.seed,
+                                      p.offset);
+              v0 = r.x;
+              if (pp + 1 < p.N) v1 = r.y;
+              if (pp + 2 < p.N) v2 = r.z;
+              if (pp + 3 < p.N) v3 = r.w;
+            }
+          }
+          float* d = sX + jl * p.xS + 4 * qd;
+          d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
+        }
       }
     }
     __syncthreads();
@@ -283,7 +317,9 @@ noise_fused_kernel(NoiseFusedParams p) {
       for (int it = 0; it < 2; ++it) {
         const int e = tid + it * kNfThreads;
         if (e < nq_out) {
-          const int ql = e / nq, qd = e - ql * nq;
+          int ql, qd;
+          if (p.nq_shift >= 0) { ql = e >> p.nq_shift; qd = e & (nq - 1); }
+          else { ql = e / nq; qd = e - ql * nq; }
           const int t = (q0 + ql) * frame + 4 * qd;
           if (q0 + ql < p.F && t + 3 < p.N &&
               (reinterpret_cast<uintptr_t>(outb + t) & 15) == 0)
@@ -295,32 +331,50 @@ noise_fused_kernel(NoiseFusedParams p) {
     // ---- D. FIR (lane = frame, warp = 16-output block), E. overlap-add ----
     {
       const float* xrow = sX + lane * p.xS;
-      const float* hrow = sH + lane * p.hS + kNfPad;
+      const float* hE = sH + lane * p.hS + kNfPad;          // h[t] at hE[t]
+      const float* hO = sH + (32 + lane) * p.hS + kNfPad;   // h[t] at hO[t + 1]
       const int nchunk = (frame + 15) >> 4;
       for (int round = 0; round * kNfWarps < p.nblk; ++round) {
         const int blk = round * kNfWarps + warp;
         const int n0 = blk * kNfR;
-        float acc[kNfR];
+        float2 acc2[8];
 #pragma unroll
-        for (int c = 0; c < kNfR; ++c) acc[c] = 0.f;
+        for (int c = 0; c < 8; ++c) acc2[c] = make_float2(0.f, 0.f);
         if (blk < p.nblk) {
           const int i_lo = max(0, n0 - (S - 1));
           const int i_hi = min(frame - 1, n0 + kNfR - 1);
-          for (int ch = i_lo >> 4; ch <= (i_hi >> 4) && ch < nchunk; ++ch) {
+          const int ch_lo = i_lo >> 4;
+          const int ch_hi = min(i_hi >> 4, nchunk - 1);
+          // windows for i = 16 * ch_lo: even-aligned pairs (h[b+2c], h[b+2c+1]),
+          // odd-aligned pairs (h[b-1+2c], h[b+2c]) with b = n0 - i (even)
+          int bse = n0 - (ch_lo << 4);
+          float2 WE[8], WO[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            WE[r] = *reinterpret_cast<const float2*>(hE + bse + 2 * r);
+            WO[r] = *reinterpret_cast<const float2*>(hO + bse + 2 * r);
+          }
+          for (int ch = ch_lo; ch <= ch_hi; ++ch) {
             const int ib = ch << 4;
-            float W[kNfR];
 #pragma unroll
-            for (int r = 0; r < kNfR; ++r) W[r] = hrow[n0 + r - ib];
+            for (int e = 0; e < 8; ++e) {          // inputs ib + 2e, ib + 2e + 1
+              const float2 xv = *reinterpret_cast<const float2*>(xrow + ib + 2 * e);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float xv = xrow[ib + u];
+              for (int c = 0; c < 8; ++c)
+                acc2[c] = nf_ffma2(xv.x, WE[(c - e) & 7], acc2[c]);
 #pragma unroll
-              for (int c = 0; c < kNfR; ++c)
-                acc[c] = fmaf(xv, W[(c - u) & 15], acc[c]);
-              W[(-u - 1) & 15] = hrow[n0 - (ib + u + 1)];
+              for (int c = 0; c < 8; ++c)
+                acc2[c] = nf_ffma2(xv.y, WO[(c - e) & 7], acc2[c]);
+              // slide both windows by one pair (two taps)
+              const int nb2 = n0 - ib - 2 * e - 2;
+              WE[(-e - 1) & 7] = *reinterpret_cast<const float2*>(hE + nb2);
+              WO[(-e - 1) & 7] = *reinterpret_cast<const float2*>(hO + nb2);
             }
           }
         }
+        float acc[kNfR];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { acc[2 * c] = acc2[c].x; acc[2 * c + 1] = acc2[c].y; }
         // overlap-add: position o = frame * lane + n, stored skewed by o / frame
         // so lanes hit distinct banks.  Blocks of one frame-group cannot collide.
         const int grp = n0 / frame;
@@ -340,12 +394,14 @@ noise_fused_kernel(NoiseFusedParams p) {
     {
       int it = 0;
       for (int e = tid; e < nq_out; e += kNfThreads, ++it) {
-        const int ql = e / nq, qd = e - ql * nq;
+        int ql, qd;
+        if (p.nq_shift >= 0) { ql = e >> p.nq_shift; qd = e & (nq - 1); }
+        else { ql = e / nq; qd = e - ql * nq; }
         const int t = (q0 + ql) * frame + 4 * qd;
         if (t >= p.N || q0 + ql >= p.F) continue;
         const int r0 = 4 * qd + p.start;
-        const int f0 = r0 / frame;
-        const int rem = r0 - f0 * frame;
+        int f0 = 0, rem = r0;                        // r0 < frame + start
+        while (rem >= frame) { rem -= frame; ++f0; }
         const int o = (ql + p.Hb) * frame + r0;     // unskewed OLA position
         const int sk = ql + p.Hb + f0;               // skew = position / frame
         float v[4];
@@ -400,8 +456,11 @@ inline bool nf_configure(NoiseFusedParams& p, int F, int nb, int N,
   p.ne = (nb + 1) / 2;
   p.no = (nb - 1) / 2;
   p.mS = nf_odd(nb);
-  p.hS = nf_odd(S + 2 * kNfPad);
-  p.xS = nf_odd(((p.frame + 15) & ~15) + 16);
+  p.hS = ((S + 2 * kNfPad + 2 + 3) & ~3) + 2;          // = 2 mod 4: conflict-free LDS.64
+  p.xS = ((((p.frame + 15) & ~15) + 16 + 3) & ~3) + 2;
+  p.nq_shift = -1;
+  for (int sh = 0; sh < 12; ++sh)
+    if ((p.frame >> 2) == (1 << sh)) p.nq_shift = sh;
   p.nblk = (p.ylen + kNfR - 1) / kNfR;
   p.ngrp = (p.nblk * kNfR + p.frame - 1) / p.frame;
   p.outLen = (p.frame + 1) * (32 + p.ngrp) + 16;

@@ -158,7 +158,7 @@ def test_fused_decoder_equals_sum_of_parts(c2):
 def test_in_kernel_noise_statistics():
   x = _np(core.uniform_noise(8, N, seed=5))
   assert x.min() >= -1.0 and x.max() < 1.0
-  assert abs(x.mean()) < 2e-3 and abs(x.var() - 1.0 / 3.0) < 2e-3
+  assert abs(x.mean()) < 5e-3 and abs(x.var() - 1.0 / 3.0) < 3e-3
   # neighbouring samples and neighbouring items are uncorrelated
-  assert abs(np.mean(x[:, 1:] * x[:, :-1])) < 2e-3
+  assert abs(np.mean(x[:, 1:] * x[:, :-1])) < 3e-3
   assert abs(np.mean(x[0] * x[1])) < 5e-3
