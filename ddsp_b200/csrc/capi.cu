@@ -10,8 +10,10 @@
 #include "controls.cuh"
 #include "harmonic.cuh"
 #include "harmonic_fast.cuh"
+#include "harmonic_pipe.cuh"
 #include "noise.cuh"
 #include "noise_fused.cuh"
+#include "noise_pipe.cuh"
 
 namespace ddsp {
 
@@ -126,6 +128,8 @@ int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
   p.ctl_flags = 0;
   cudaStream_t st = (cudaStream_t)stream;
 
+  if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_pipe_supported(p))
+    return launch_harmonic_pipe(p, st);
   if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_fast_supported(p)) {
     int rc = launch_harmonic_fast(p, st);
     if (rc != 1) return rc;   // 1 = declined, fall through to the generic path
@@ -288,8 +292,8 @@ int ddsp_b200_filtered_noise_forward(const float* mags, const float* noise,
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (noise_fused_supported(F, nb, N, window_size)) {
-    return launch_noise_fused(mags, noise, seed, offset, audio, B, F, nb, N,
-                              window_size, accumulate, st);
+    return launch_noise_best(mags, noise, seed, offset, audio, B, F, nb, N,
+                             window_size, accumulate, st);
   }
   const size_t need = ddsp_b200_filtered_noise_workspace(B, F, nb, N, window_size);
   DDSP_REQUIRE(workspace != nullptr && workspace_bytes >= need,
@@ -354,15 +358,16 @@ int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
                "decoder_forward: shape outside the fused decoder path "
                "(needs hop %% 64 == 0, n_frequencies <= %d)", kNfMaxNb);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_harmonic_fast(p, st);
+  int rc = harmonic_pipe_supported(p) ? launch_harmonic_pipe(p, st)
+                                      : launch_harmonic_fast(p, st);
   if (rc == 1) {
     set_error("decoder_forward: harmonic tile does not fit shared memory");
     return DDSP_B200_E_UNSUPPORTED;
   }
   if (rc) return rc;
-  return launch_noise_fused(mags_raw, noise, seed, offset, audio, B, F, nb, N,
-                            window_size, /*accumulate=*/1, st, /*raw=*/1,
-                            initial_bias);
+  return launch_noise_best(mags_raw, noise, seed, offset, audio, B, F, nb, N,
+                           window_size, /*accumulate=*/1, st, /*raw=*/1,
+                           initial_bias);
 }
 
 int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,

@@ -56,43 +56,6 @@ __host__ __device__ inline FastSmem fast_smem_layout(int FT, int Kp, int hop) {
   return s;
 }
 
-// --- mbarrier / TMA bulk copy (PTX) -----------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(void* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src,
-                                             uint32_t bytes, void* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, uint32_t phase) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(phase)
-      : "memory");
-}
-
 // Slow, exact per-oscillator evaluation of one sample (frames with f0 < 1 Hz,
 // where the live-count shortcut is not valid).
 __device__ __noinline__ float harmonic_sample_exact(const float* x0,
@@ -168,6 +131,157 @@ __device__ __forceinline__ void osc2_step(Osc2& st) {
   st.d2 = ffma2(st.nalpha, st.v2, st.d2);
   st.v1 = fadd2(st.v1, st.d1);
   st.v2 = fadd2(st.v2, st.d2);
+}
+
+// One frame (hop samples, 64 per pass) of one batch item, executed by one warp.
+// x0 / x1: the frame's two harmonic-distribution rows in shared memory.
+__device__ __forceinline__ void harmonic_frame_pass(
+    const float* __restrict__ x0, const float* __restrict__ x1,
+    unsigned long long Pi, unsigned long long Ai, unsigned long long Di,
+    int kc_a, int kc_b, float f_lo, float f_hi, float amp0, float amp1,
+    const float* __restrict__ sW, const float2* __restrict__ sTab, int K,
+    float nyquist, int hop, int lane, float* __restrict__ out, int accumulate) {
+  const float inv_hop = 1.0f / (float)hop;
+  for (int r0 = 0; r0 < hop; r0 += 64) {
+    const int ra = r0 + lane, rb = ra + 32;
+    // fundamental phase, 64-bit fixed point turns (inclusive cumsum)
+    const unsigned long long pha = Pi + (unsigned long long)(ra + 1) * Ai +
+        (unsigned long long)(((long long)ra * (ra + 1)) >> 1) * Di;
+    const unsigned long long phb = Pi + (unsigned long long)(rb + 1) * Ai +
+        (unsigned long long)(((long long)rb * (rb + 1)) >> 1) * Di;
+    const uint32_t pa = (uint32_t)((pha + 0x80000000ull) >> 32);
+    const uint32_t pb = (uint32_t)((phb + 0x80000000ull) >> 32);
+    const float w1a_ = sW[ra], w1b_ = sW[rb];
+    const float w0a = (1.0f - w1a_) * amp0, w1a = w1a_ * amp1;
+    const float w0b = (1.0f - w1b_) * amp0, w1b = w1b_ * amp1;
+    float ya, yb;
+    if (kc_a < 0) {
+      ya = harmonic_sample_exact(x0, x1, w0a, w1a, pa, f_lo, f_hi,
+                                 (float)ra * inv_hop, K, nyquist);
+      yb = harmonic_sample_exact(x0, x1, w0b, w1b, pb, f_lo, f_hi,
+                                 (float)rb * inv_hop, K, nyquist);
+    } else {
+      int ka = kc_a, kb = kc_a, kmin = kc_a, kmax = kc_a;
+      if (kc_a != kc_b) {      // live count changes inside this frame
+        ka = live_harmonics(f_lo, f_hi, (float)ra * inv_hop, K, nyquist);
+        kb = live_harmonics(f_lo, f_hi, (float)rb * inv_hop, K, nyquist);
+        kmin = __reduce_min_sync(0xffffffffu, min(ka, kb));
+        kmax = __reduce_max_sync(0xffffffffu, max(ka, kb));
+      }
+      Osc2 st;
+      osc2_init(st, pa, pb, sTab);
+      const int k_main = kmin & ~3;            // harmonics 1..k_main unmasked
+      int k = 0;
+#pragma unroll 2
+      for (; k < k_main; k += 4) {
+        const float4 X0 = *reinterpret_cast<const float4*>(x0 + k);
+        const float4 X1 = *reinterpret_cast<const float4*>(x1 + k);
+        st.a0e1 = ffma2(bc2(X0.x), st.v1, st.a0e1);
+        st.a0e2 = ffma2(bc2(X0.y), st.v2, st.a0e2);
+        st.a1e1 = ffma2(bc2(X1.x), st.v1, st.a1e1);
+        st.a1e2 = ffma2(bc2(X1.y), st.v2, st.a1e2);
+        osc2_step(st);
+        st.a0o1 = ffma2(bc2(X0.z), st.v1, st.a0o1);
+        st.a0o2 = ffma2(bc2(X0.w), st.v2, st.a0o2);
+        st.a1o1 = ffma2(bc2(X1.z), st.v1, st.a1o1);
+        st.a1o2 = ffma2(bc2(X1.w), st.v2, st.a1o2);
+        osc2_step(st);
+      }
+      for (; k < kmax; k += 4) {               // masked tail (<= 2 passes)
+        const float4 X0 = *reinterpret_cast<const float4*>(x0 + k);
+        const float4 X1 = *reinterpret_cast<const float4*>(x1 + k);
+        // harmonic numbers k+1 .. k+4; live iff number <= ka (sample a) / kb
+        const float2 m1 = make_float2(k + 1 <= ka ? 1.f : 0.f, k + 1 <= kb ? 1.f : 0.f);
+        const float2 m2 = make_float2(k + 2 <= ka ? 1.f : 0.f, k + 2 <= kb ? 1.f : 0.f);
+        const float2 m3 = make_float2(k + 3 <= ka ? 1.f : 0.f, k + 3 <= kb ? 1.f : 0.f);
+        const float2 m4 = make_float2(k + 4 <= ka ? 1.f : 0.f, k + 4 <= kb ? 1.f : 0.f);
+        float2 u1 = fmul2(st.v1, m1), u2 = fmul2(st.v2, m2);
+        st.a0e1 = ffma2(bc2(X0.x), u1, st.a0e1);
+        st.a0e2 = ffma2(bc2(X0.y), u2, st.a0e2);
+        st.a1e1 = ffma2(bc2(X1.x), u1, st.a1e1);
+        st.a1e2 = ffma2(bc2(X1.y), u2, st.a1e2);
+        osc2_step(st);
+        u1 = fmul2(st.v1, m3); u2 = fmul2(st.v2, m4);
+        st.a0o1 = ffma2(bc2(X0.z), u1, st.a0o1);
+        st.a0o2 = ffma2(bc2(X0.w), u2, st.a0o2);
+        st.a1o1 = ffma2(bc2(X1.z), u1, st.a1o1);
+        st.a1o2 = ffma2(bc2(X1.w), u2, st.a1o2);
+        osc2_step(st);
+      }
+      {
+        const float2 r0s = ffma2(st.sigma, fadd2(st.a0o1, st.a0o2),
+                                 fadd2(st.a0e1, st.a0e2));
+        const float2 r1s = ffma2(st.sigma, fadd2(st.a1o1, st.a1o2),
+                                 fadd2(st.a1e1, st.a1e2));
+        const float2 y = ffma2(r1s, make_float2(w1a, w1b),
+                               fmul2(r0s, make_float2(w0a, w0b)));
+        ya = y.x;
+        yb = y.y;
+      }
+    }
+    float* o = out + r0;
+    if (accumulate) {
+      ya += o[lane];
+      yb += o[lane + 32];
+    }
+    o[lane] = ya;
+    o[lane + 32] = yb;
+  }
+}
+
+// Harmonic.get_controls for up to four frame rows held in shared memory, by one
+// warp (8 lanes per row): exp_sigmoid, frame-rate Nyquist mask on float32 f0*k,
+// row normalisation with safe_divide (synths.py:110-117, core.py:894-907).  A
+// row's live harmonics are a prefix (f0*k is monotone in k), so only
+// ceil(live/4) float4 groups pay for exp_sigmoid - about a quarter of the row at
+// the benchmark's f0 range.
+__device__ __forceinline__ void harmonic_controls_rows(
+    float* __restrict__ sX, const float* __restrict__ sF0, int r0, int rows_in,
+    int K, int Kp, float nyquist, bool raw_scale, bool nyq, int lane) {
+  const int K4 = Kp >> 2;                      // float4 groups per row
+  const int sub = lane >> 3, l8 = lane & 7;
+  const int r = r0 + sub;
+  const bool row_ok = r < rows_in;
+  float4* row4 = reinterpret_cast<float4*>(sX + (row_ok ? r : r0) * Kp);
+  const float f = sF0[row_ok ? r : r0];
+  int live = K;                                // harmonics with f0*k < sr/2
+  if (nyq && f > 0.f) {
+    int k = (int)fminf(nyquist / f, (float)K);
+    while (k < K && __fmul_rn(f, (float)(k + 1)) < nyquist) ++k;
+    while (k > 0 && !(__fmul_rn(f, (float)k) < nyquist)) --k;
+    live = k;
+  }
+  float sum = 0.f;
+  if (row_ok) {
+    for (int c4 = l8; c4 < K4; c4 += 8) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * c4 < live) {
+        v = row4[c4];
+        float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float w = e[u];
+          if (raw_scale) w = exp_sigmoid_f(w);
+          if (4 * c4 + u >= live) w = 0.f;
+          e[u] = w;
+          sum += w;
+        }
+        v = make_float4(e[0], e[1], e[2], e[3]);
+      }
+      row4[c4] = v;
+    }
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  const float inv = 1.0f / ((sum == 0.0f) ? 1e-7f : sum);
+  if (row_ok) {
+    for (int c4 = l8; 4 * c4 < live; c4 += 8) {
+      float4 v = row4[c4];
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      row4[c4] = v;
+    }
+  }
 }
 
 template <bool WINDOW>
@@ -301,34 +415,9 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
     // exp_sigmoid, frame-rate Nyquist mask on float32 f0*k, row normalisation
     // with safe_divide.  One warp per frame row, rows stay in shared memory.
     const bool nyq = p.ctl_flags & DDSP_B200_CTL_NYQUIST;
-    const int K4 = Kp >> 2;                      // float4 groups per row
-    for (int r = warp; r < rows_in; r += kFastThreads / 32) {
-      float4* row4 = reinterpret_cast<float4*>(sX + r * Kp);
-      const float f = sF0[r];
-      float sum = 0.f;
-      for (int c4 = lane; c4 < K4; c4 += 32) {
-        float4 v = row4[c4];
-        float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = 4 * c4 + u;
-          float w = e[u];
-          if (raw_scale) w = exp_sigmoid_f(w);
-          if (c >= K || (nyq && __fmul_rn(f, (float)(c + 1)) >= p.nyquist)) w = 0.f;
-          e[u] = w;
-          sum += w;
-        }
-        row4[c4] = make_float4(e[0], e[1], e[2], e[3]);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float inv = 1.0f / ((sum == 0.0f) ? 1e-7f : sum);
-      for (int c4 = lane; c4 < K4; c4 += 32) {
-        float4 v = row4[c4];
-        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-        row4[c4] = v;
-      }
-    }
+    for (int r0 = warp * 4; r0 < rows_in; r0 += (kFastThreads / 32) * 4)
+      harmonic_controls_rows(sX, sF0, r0, rows_in, K, Kp, p.nyquist, raw_scale, nyq,
+                             lane);
     __syncthreads();
   }
   if (rows_in < nfr + 1) {                    // frame F := frame F-1
@@ -338,100 +427,12 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   }
 
   // ---- 4. samples: warp w takes frames w, w+8, ...; 64 samples per pass ----
-  const float inv_hop = 1.0f / (float)hop;
   float* outb = p.audio + (size_t)b * p.N + (size_t)i0 * hop;
   for (int li = warp; li < nfr; li += kFastThreads / 32) {
-    const float f_lo = sF0[li], f_hi = sF0[li + 1];
-    const float amp0 = sAmp[li], amp1 = sAmp[li + 1];
-    const unsigned long long Pi = sP[li], Ai = sA[li], Di = sD[li];
-    const int kc_a = sKc[2 * li], kc_b = sKc[2 * li + 1];
-    const float* x0 = sX + li * Kp;
-    const float* x1 = x0 + Kp;
-    for (int r0 = 0; r0 < hop; r0 += 64) {
-      const int ra = r0 + lane, rb = ra + 32;
-      // fundamental phase, 64-bit fixed point turns (inclusive cumsum)
-      const unsigned long long pha = Pi + (unsigned long long)(ra + 1) * Ai +
-          (unsigned long long)(((long long)ra * (ra + 1)) >> 1) * Di;
-      const unsigned long long phb = Pi + (unsigned long long)(rb + 1) * Ai +
-          (unsigned long long)(((long long)rb * (rb + 1)) >> 1) * Di;
-      const uint32_t pa = (uint32_t)((pha + 0x80000000ull) >> 32);
-      const uint32_t pb = (uint32_t)((phb + 0x80000000ull) >> 32);
-      const float w1a_ = sW[ra], w1b_ = sW[rb];
-      const float w0a = (1.0f - w1a_) * amp0, w1a = w1a_ * amp1;
-      const float w0b = (1.0f - w1b_) * amp0, w1b = w1b_ * amp1;
-      float ya, yb;
-      if (kc_a < 0) {
-        ya = harmonic_sample_exact(x0, x1, w0a, w1a, pa, f_lo, f_hi,
-                                   (float)ra * inv_hop, K, p.nyquist);
-        yb = harmonic_sample_exact(x0, x1, w0b, w1b, pb, f_lo, f_hi,
-                                   (float)rb * inv_hop, K, p.nyquist);
-      } else {
-        int ka = kc_a, kb = kc_a, kmin = kc_a, kmax = kc_a;
-        if (kc_a != kc_b) {      // live count changes inside this frame
-          ka = live_harmonics(f_lo, f_hi, (float)ra * inv_hop, K, p.nyquist);
-          kb = live_harmonics(f_lo, f_hi, (float)rb * inv_hop, K, p.nyquist);
-          kmin = __reduce_min_sync(0xffffffffu, min(ka, kb));
-          kmax = __reduce_max_sync(0xffffffffu, max(ka, kb));
-        }
-        Osc2 st;
-        osc2_init(st, pa, pb, sTab);
-        const int k_main = kmin & ~3;            // harmonics 1..k_main unmasked
-        int k = 0;
-#pragma unroll 2
-        for (; k < k_main; k += 4) {
-          const float4 X0 = *reinterpret_cast<const float4*>(x0 + k);
-          const float4 X1 = *reinterpret_cast<const float4*>(x1 + k);
-          st.a0e1 = ffma2(bc2(X0.x), st.v1, st.a0e1);
-          st.a0e2 = ffma2(bc2(X0.y), st.v2, st.a0e2);
-          st.a1e1 = ffma2(bc2(X1.x), st.v1, st.a1e1);
-          st.a1e2 = ffma2(bc2(X1.y), st.v2, st.a1e2);
-          osc2_step(st);
-          st.a0o1 = ffma2(bc2(X0.z), st.v1, st.a0o1);
-          st.a0o2 = ffma2(bc2(X0.w), st.v2, st.a0o2);
-          st.a1o1 = ffma2(bc2(X1.z), st.v1, st.a1o1);
-          st.a1o2 = ffma2(bc2(X1.w), st.v2, st.a1o2);
-          osc2_step(st);
-        }
-        for (; k < kmax; k += 4) {               // masked tail (<= 2 passes)
-          const float4 X0 = *reinterpret_cast<const float4*>(x0 + k);
-          const float4 X1 = *reinterpret_cast<const float4*>(x1 + k);
-          // harmonic numbers k+1 .. k+4; live iff number <= ka (sample a) / kb
-          const float2 m1 = make_float2(k + 1 <= ka ? 1.f : 0.f, k + 1 <= kb ? 1.f : 0.f);
-          const float2 m2 = make_float2(k + 2 <= ka ? 1.f : 0.f, k + 2 <= kb ? 1.f : 0.f);
-          const float2 m3 = make_float2(k + 3 <= ka ? 1.f : 0.f, k + 3 <= kb ? 1.f : 0.f);
-          const float2 m4 = make_float2(k + 4 <= ka ? 1.f : 0.f, k + 4 <= kb ? 1.f : 0.f);
-          float2 u1 = fmul2(st.v1, m1), u2 = fmul2(st.v2, m2);
-          st.a0e1 = ffma2(bc2(X0.x), u1, st.a0e1);
-          st.a0e2 = ffma2(bc2(X0.y), u2, st.a0e2);
-          st.a1e1 = ffma2(bc2(X1.x), u1, st.a1e1);
-          st.a1e2 = ffma2(bc2(X1.y), u2, st.a1e2);
-          osc2_step(st);
-          u1 = fmul2(st.v1, m3); u2 = fmul2(st.v2, m4);
-          st.a0o1 = ffma2(bc2(X0.z), u1, st.a0o1);
-          st.a0o2 = ffma2(bc2(X0.w), u2, st.a0o2);
-          st.a1o1 = ffma2(bc2(X1.z), u1, st.a1o1);
-          st.a1o2 = ffma2(bc2(X1.w), u2, st.a1o2);
-          osc2_step(st);
-        }
-        {
-          const float2 r0s = ffma2(st.sigma, fadd2(st.a0o1, st.a0o2),
-                                   fadd2(st.a0e1, st.a0e2));
-          const float2 r1s = ffma2(st.sigma, fadd2(st.a1o1, st.a1o2),
-                                   fadd2(st.a1e1, st.a1e2));
-          const float2 y = ffma2(r1s, make_float2(w1a, w1b),
-                                 fmul2(r0s, make_float2(w0a, w0b)));
-          ya = y.x;
-          yb = y.y;
-        }
-      }
-      float* o = outb + (size_t)li * hop + r0;
-      if (p.accumulate) {
-        ya += o[lane];
-        yb += o[lane + 32];
-      }
-      o[lane] = ya;
-      o[lane + 32] = yb;
-    }
+    harmonic_frame_pass(sX + li * Kp, sX + (li + 1) * Kp, sP[li], sA[li], sD[li],
+                        sKc[2 * li], sKc[2 * li + 1], sF0[li], sF0[li + 1],
+                        sAmp[li], sAmp[li + 1], sW, sTab, K, p.nyquist, hop, lane,
+                        outb + (size_t)li * hop, p.accumulate);
   }
 }
 

@@ -543,6 +543,33 @@ def decoder(amps, harmonic_distribution, f0_hz, noise_magnitudes, noise,
 
 
 # ----------------------------------------------------------------------------
+# Multi-scale spectral loss (losses.py:102-243, spectral_ops.py:34-70)
+# ----------------------------------------------------------------------------
+def stft_mag(audio, frame_size, overlap=0.75):
+  """|tf.signal.stft(frame_length, frame_step, pad_end=True)| with the default
+  periodic Hann window (spectral_ops.py:34-47, 67-70)."""
+  audio = np.asarray(audio, np.float64)
+  step = int(frame_size * (1.0 - overlap))
+  frames = frame_pad_end(audio, frame_size, step)
+  window = hann_window(frame_size, np.float64)
+  return np.abs(np.fft.rfft(frames * window, frame_size, axis=-1))
+
+
+def spectral_loss(target_audio, audio, fft_sizes=(2048, 1024, 512, 256, 128, 64),
+                  mag_weight=1.0, logmag_weight=0.0):
+  """SpectralLoss.call with loss_type='L1' (losses.py:194-243)."""
+  loss = 0.0
+  for size in fft_sizes:
+    t = stft_mag(target_audio, size)
+    v = stft_mag(audio, size)
+    if mag_weight > 0:
+      loss += mag_weight * np.mean(np.abs(t - v))
+    if logmag_weight > 0:
+      loss += logmag_weight * np.mean(np.abs(safe_log(t) - safe_log(v)))
+  return loss
+
+
+# ----------------------------------------------------------------------------
 # Philox4x32-10 restatement (Salmon et al. 2011, Random123), used to check the
 # in-kernel noise generator bit-for-bit.  Not part of the reference (the
 # reference draws tf.random.uniform, synths.py:192-193, unseeded).

@@ -25,7 +25,9 @@ def _np(x):
 
 @pytest.mark.parametrize('B,F,K,N', [(1, 250, 64, 16000), (3, 100, 100, 6400),
                                      (2, 50, 99, 3200), (2, 40, 1, 2560),
-                                     (2, 10, 16, 1000), (1, 7, 5, 7 * 33)])
+                                     (2, 10, 16, 1000), (1, 7, 5, 7 * 33),
+                                     (200, 40, 8, 2560), (5, 33, 12, 33 * 64),
+                                     (3, 64, 128, 4096)])
 @pytest.mark.parametrize('amp_method', ['window', 'linear'])
 @pytest.mark.parametrize('phase_mode', ['recurrence', 'direct'])
 def test_harmonic_synthesis_matches_oracle(B, F, K, N, amp_method, phase_mode):
@@ -107,7 +109,10 @@ def test_frequency_impulse_response(nb, ws):
 @pytest.mark.parametrize('B,F,nb,N,ws', [(2, 100, 65, 6400, 0), (2, 25, 65, 1600, 257),
                                          (1, 13, 513, 1000, 257), (2, 1, 513, 1000, 257),
                                          (1, 1000, 513, 1000, 257), (3, 50, 100, 50, 257),
-                                         (2, 20, 256, 1280, 257), (1, 1000, 65, 64000, 0)])
+                                         (2, 20, 256, 1280, 257), (1, 1000, 65, 64000, 0),
+                                         (1, 30, 65, 1920, 0), (3, 58, 65, 3712, 257),
+                                         (2, 29, 65, 1856, 0), (2, 5, 65, 320, 0),
+                                         (2, 40, 33, 2560, 0), (1, 24, 65, 3072, 0)])
 def test_filtered_noise_matches_oracle(B, F, nb, N, ws):
   rng = np.random.default_rng(B + F + nb)
   mags = rng.uniform(0.0, 1.0, (B, F, nb)).astype(np.float32)
