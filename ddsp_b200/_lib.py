@@ -56,6 +56,10 @@ SIGNATURES = {
     'ddsp_b200_decoder_forward':
         (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _f,
               _i, _i, _i, _f, _vp]),
+    'ddsp_b200_harmonic_backward':
+        (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'ddsp_b200_filtered_noise_backward':
+        (_i, [_vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _vp]),
     'ddsp_b200_add': (_i, [_vp, _vp, _vp, _i64, _vp]),
 }
 

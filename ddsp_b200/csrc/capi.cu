@@ -10,10 +10,10 @@
 #include "controls.cuh"
 #include "harmonic.cuh"
 #include "harmonic_fast.cuh"
-#include "harmonic_pipe.cuh"
 #include "noise.cuh"
 #include "noise_fused.cuh"
 #include "noise_pipe.cuh"
+#include "backward.cuh"
 
 namespace ddsp {
 
@@ -128,8 +128,6 @@ int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
   p.ctl_flags = 0;
   cudaStream_t st = (cudaStream_t)stream;
 
-  if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_pipe_supported(p))
-    return launch_harmonic_pipe(p, st);
   if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_fast_supported(p)) {
     int rc = launch_harmonic_fast(p, st);
     if (rc != 1) return rc;   // 1 = declined, fall through to the generic path
@@ -358,8 +356,7 @@ int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
                "decoder_forward: shape outside the fused decoder path "
                "(needs hop %% 64 == 0, n_frequencies <= %d)", kNfMaxNb);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = harmonic_pipe_supported(p) ? launch_harmonic_pipe(p, st)
-                                      : launch_harmonic_fast(p, st);
+  int rc = launch_harmonic_fast(p, st);
   if (rc == 1) {
     set_error("decoder_forward: harmonic tile does not fit shared memory");
     return DDSP_B200_E_UNSUPPORTED;
@@ -368,6 +365,93 @@ int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
   return launch_noise_best(mags_raw, noise, seed, offset, audio, B, F, nb, N,
                            window_size, /*accumulate=*/1, st, /*raw=*/1,
                            initial_bias);
+}
+
+int ddsp_b200_harmonic_backward(const float* f0_hz, const float* grad_audio,
+                                float* g0, float* g1, int B, int F, int K, int N,
+                                float sample_rate, int amp_method, void* stream) {
+  DDSP_REQUIRE(f0_hz && grad_audio && g0 && g1, DDSP_B200_E_INVALID,
+               "harmonic_backward: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && K >= 1 && N >= 1 && N % F == 0,
+               DDSP_B200_E_INVALID,
+               "harmonic_backward: bad shape B=%d F=%d K=%d N=%d", B, F, K, N);
+  DDSP_REQUIRE(amp_method == DDSP_B200_AMP_WINDOW ||
+                   amp_method == DDSP_B200_AMP_LINEAR,
+               DDSP_B200_E_INVALID, "harmonic_backward: bad amp_method %d",
+               amp_method);
+  DDSP_REQUIRE(sample_rate > 0.f, DDSP_B200_E_INVALID,
+               "harmonic_backward: sample_rate must be positive");
+  if (B == 0) return 0;
+  HarmonicParams p;
+  p.f0 = f0_hz; p.amps = nullptr; p.hd = nullptr; p.audio = nullptr;
+  p.B = B; p.F = F; p.K = K; p.N = N; p.hop = N / F;
+  p.sample_rate = sample_rate; p.nyquist = sample_rate * 0.5f;
+  p.inv_sr = 1.0 / (double)sample_rate;
+  p.amp_method = amp_method; p.accumulate = 0; p.ctl_flags = 0; p.Kp = K;
+  DDSP_REQUIRE(p.hop % 64 == 0 && p.hop <= 8192 && B <= 65535,
+               DDSP_B200_E_UNSUPPORTED,
+               "harmonic_backward: needs hop %% 64 == 0 (hop = %d)", p.hop);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t gbytes = sizeof(float) * (size_t)B * F * K;
+  cudaMemsetAsync(g0, 0, gbytes, st);
+  cudaMemsetAsync(g1, 0, gbytes, st);
+  p.FT = std::max(1, std::min(F, 2048 / p.hop));
+  const size_t smem = harmonic_backward_smem(p.FT, p.hop);
+  dim3 grid((F + p.FT - 1) / p.FT, B);
+  if (amp_method == DDSP_B200_AMP_WINDOW) {
+    int rc = set_smem(harmonic_backward_kernel<true>, smem, "harmonic_backward");
+    if (rc) return rc;
+    harmonic_backward_kernel<true><<<grid, kHbThreads, smem, st>>>(p, grad_audio, g0, g1);
+  } else {
+    int rc = set_smem(harmonic_backward_kernel<false>, smem, "harmonic_backward");
+    if (rc) return rc;
+    harmonic_backward_kernel<false><<<grid, kHbThreads, smem, st>>>(p, grad_audio, g0, g1);
+  }
+  DDSP_CHECK_LAUNCH("harmonic_backward");
+  return 0;
+}
+
+int ddsp_b200_filtered_noise_backward(const float* grad_audio, const float* noise,
+                                      uint64_t seed, uint64_t offset, float* dmags,
+                                      int B, int F, int nb, int N, int window_size,
+                                      void* stream) {
+  DDSP_REQUIRE(grad_audio && dmags, DDSP_B200_E_INVALID,
+               "filtered_noise_backward: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && N >= 1 && nb >= 2, DDSP_B200_E_INVALID,
+               "filtered_noise_backward: bad shape B=%d F=%d nb=%d N=%d", B, F, nb, N);
+  const int frame = (N + F - 1) / F;
+  DDSP_REQUIRE((N + frame - 1) / frame == F, DDSP_B200_E_INVALID,
+               "filtered_noise_backward: %d frames do not tile %d samples", F, N);
+  if (B == 0) return 0;
+  NoiseBwdParams p;
+  p.grad = grad_audio; p.noise = noise; p.dmags = dmags;
+  p.seed = seed; p.offset = offset;
+  p.B = B; p.F = F; p.nb = nb; p.N = N; p.frame = frame;
+  p.g = make_ir_geom(nb, window_size);
+  p.S = p.g.S;
+  p.start = (p.S - 1) / 2 - 1;
+  DDSP_REQUIRE(p.start >= 0, DDSP_B200_E_UNSUPPORTED,
+               "filtered_noise_backward: impulse response too short");
+  p.ylen = frame + p.S - 1;
+  p.nh = p.g.S0 / 2 + 1;
+  p.xS = frame | 1;
+  p.gS = p.ylen | 1;
+  p.hS = (p.S + p.nh) | 1;
+  p.tiles_per_item = (F + 31) / 32;
+  const long long n_tiles = (long long)B * p.tiles_per_item;
+  DDSP_REQUIRE(n_tiles < (1ll << 31), DDSP_B200_E_INVALID,
+               "filtered_noise_backward: too many tiles");
+  p.n_tiles = (int)n_tiles;
+  const size_t smem = sizeof(float) * ((size_t)p.g.S0 + p.S + 32 * (size_t)(p.xS + p.gS + p.hS));
+  DDSP_REQUIRE(smem <= kMaxDynSmem, DDSP_B200_E_UNSUPPORTED,
+               "filtered_noise_backward: shape needs %zu B of shared memory", smem);
+  int rc = set_smem(noise_backward_kernel, smem, "filtered_noise_backward");
+  if (rc) return rc;
+  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  const int grid = (int)std::min<long long>(n_tiles, (long long)kNumSMs * per_sm);
+  noise_backward_kernel<<<grid, kNbThreads, smem, (cudaStream_t)stream>>>(p);
+  DDSP_CHECK_LAUNCH("filtered_noise_backward");
+  return 0;
 }
 
 int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,

@@ -149,6 +149,25 @@ int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
                               int harmonic_flags, int window_size,
                               float initial_bias, void* stream);
 
+/* Backward of Harmonic.get_signal w.r.t. the frame-rate harmonic amplitudes
+ * ha = amplitudes * harmonic_distribution (the transpose of core.py:1096-1111;
+ * the reference gets it from TF autodiff).  grad_audio [B,N] -> g0, g1 [B,F,K]:
+ *   g0[i,k] = sum_{t in frame i} grad(t) w0(r) m_k(t) sin(k phi(t)),  g1 with w1;
+ *   dL/dha[i,k] = g0[i,k] + g1[i-1,k] (+ g1[F-1,k] when i == F-1).
+ * The frame-rate recombination is left to the caller.  d f0 is not built. */
+int ddsp_b200_harmonic_backward(const float* f0_hz, const float* grad_audio,
+                                float* g0, float* g1, int B, int F, int K, int N,
+                                float sample_rate, int amp_method, void* stream);
+
+/* Backward of FilteredNoise.get_signal w.r.t. magnitudes (controls): the
+ * transpose of core.frequency_filter (core.py:1628-1655) for the same noise
+ * (caller-supplied, or the Philox stream of (seed, offset)).
+ * grad_audio [B,N] -> dmags [B,F,nb]. */
+int ddsp_b200_filtered_noise_backward(const float* grad_audio, const float* noise,
+                                      uint64_t seed, uint64_t offset, float* dmags,
+                                      int B, int F, int nb, int N, int window_size,
+                                      void* stream);
+
 /* processors.Add.get_signal (processors.py:174-176). out may alias a or b. */
 int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,
                   void* stream);
