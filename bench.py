@@ -189,7 +189,9 @@ def run_ours(args):
   dev = torch.device('cuda', local_rank)
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-    dist.init_process_group('nccl', device_id=dev)
+    import datetime
+    dist.init_process_group('nccl', device_id=dev,
+                            timeout=datetime.timedelta(seconds=180))
   lib = _lib.load()
   B = args.batch
 
@@ -216,25 +218,27 @@ def run_ours(args):
   out_host = torch.empty((B, N_SAMPLES), dtype=torch.float32).pin_memory()
   d2h_bytes = out_host.numel() * 4
 
-  def barrier():
+  def barrier(collective=True):
     torch.cuda.synchronize()
-    if world > 1:
+    if world > 1 and collective:
       dist.barrier()
       torch.cuda.synchronize()
 
-  def timed(fn, steps, warmup):
+  def timed(fn, steps, warmup, collective=True):
+    """CUDA-event time of `steps` calls; `collective=False` for rank-local
+    measurements (no barrier / all-reduce: the other ranks are not here)."""
     for i in range(warmup):
       fn(i)
-    barrier()
+    barrier(collective)
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
       fn(warmup + i)
     e1.record()
-    barrier()
+    barrier(collective)
     ms = e0.elapsed_time(e1)
-    if world > 1:
+    if world > 1 and collective:
       tms = torch.tensor([ms], device=dev)
       dist.all_reduce(tms, op=dist.ReduceOp.MAX)
       ms = float(tms.item())
@@ -298,12 +302,39 @@ def run_ours(args):
       B3 = 256
       h3 = make_host_inputs(B3, seed=77)
       d3 = {k: torch.from_numpy(v).to(dev) for k, v in h3.items()}
-      ms3 = timed(lambda i: group(d3), 10, 3) / 10
+      ms3 = timed(lambda i: group(d3), 10, 3, collective=False) / 10
       extra['c3_batch256_samples_per_s'] = B3 * N_SAMPLES / (ms3 * 1e-3)
       extra['c3_ms_per_step'] = ms3
       del d3
     except Exception as e:  # pylint: disable=broad-except
       extra['c3_error'] = repr(e)
+    try:
+      # configs[3]: decoder forward + backward through the multi-scale
+      # SpectralLoss (ae.gin:39-41), B=128 - context only, not the headline.
+      from ddsp_b200 import autograd as ag
+      from ddsp_b200 import losses
+      B4 = 128
+      h4 = make_host_inputs(B4, seed=55)
+      d4 = {k: torch.from_numpy(v).to(dev) for k, v in h4.items()}
+      for k in ('amps', 'harmonic_distribution', 'noise_magnitudes'):
+        d4[k].requires_grad_(True)
+      target = 0.1 * torch.randn(B4, N_SAMPLES, device=dev)
+      loss_obj = losses.SpectralLoss(mag_weight=1.0, logmag_weight=1.0)
+
+      def c4_step(i):
+        for k in ('amps', 'harmonic_distribution', 'noise_magnitudes'):
+          d4[k].grad = None
+        audio = ag.decoder_train(d4['amps'], d4['harmonic_distribution'],
+                                 d4['f0_hz'], d4['noise_magnitudes'],
+                                 n_samples=N_SAMPLES, window_size=0, seed=1, offset=i)
+        loss_obj(target, audio).backward()
+
+      ms4 = timed(c4_step, 5, 2, collective=False) / 5
+      extra['c4_fwd_bwd_spectral_loss_b128_ms_per_step'] = ms4
+      extra['c4_samples_per_s'] = B4 * N_SAMPLES / (ms4 * 1e-3)
+      del d4
+    except Exception as e:  # pylint: disable=broad-except
+      extra['c4_error'] = repr(e)
 
   if rank != 0:
     if world > 1:

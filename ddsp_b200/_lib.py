@@ -42,6 +42,8 @@ SIGNATURES = {
         (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
     'ddsp_b200_harmonic_forward':
         (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
+    'ddsp_b200_streaming_harmonic_forward':
+        (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'ddsp_b200_noise_controls': (_i, [_vp, _vp, _i64, _f, _i, _vp]),
     'ddsp_b200_ir_size': (_i, [_i, _i]),
     'ddsp_b200_frequency_impulse_response':
@@ -60,6 +62,7 @@ SIGNATURES = {
         (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'ddsp_b200_filtered_noise_backward':
         (_i, [_vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _vp]),
+    'ddsp_b200_resample': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'ddsp_b200_add': (_i, [_vp, _vp, _vp, _i64, _vp]),
 }
 

@@ -118,6 +118,71 @@ def exp_sigmoid(x, exponent=10.0, max_value=2.0, threshold=1e-7):
 
 
 # ----------------------------------------------------------------------------
+# Resampling (core.py:573-714) - stand-alone ops (the synthesizers fuse them)
+# ----------------------------------------------------------------------------
+_RESAMPLE_METHODS = {'window': 0, 'linear': 1, 'nearest': 2}
+
+
+def _resample_3d(inputs, n_timesteps, method, add_endpoint):
+  inputs = torch_float32(inputs)
+  b, f, c = inputs.shape
+  out = torch.empty((b, int(n_timesteps), c), dtype=torch.float32,
+                    device=inputs.device)
+  _lib.check(_lib.load().ddsp_b200_resample(
+      _ptr(inputs), _ptr(out), b, f, c, int(n_timesteps),
+      _RESAMPLE_METHODS[method], int(bool(add_endpoint)), _stream()))
+  return out
+
+
+def upsample_with_windows(inputs, n_timesteps: int, add_endpoint: bool = True):
+  """core.upsample_with_windows (core.py:645-714)."""
+  shape = _shape(inputs)
+  if len(shape) != 3:
+    raise ValueError('Upsample_with_windows() only supports 3 dimensions, '
+                     'not {}.'.format(list(shape)))
+  n_frames = shape[1] + (1 if add_endpoint else 0)
+  n_intervals = n_frames - 1
+  if n_frames >= n_timesteps:
+    raise ValueError('Upsample with windows cannot be used for downsampling'
+                     'More input frames ({}) than output timesteps ({})'.format(
+                         n_frames, n_timesteps))
+  if n_intervals <= 0 or n_timesteps % n_intervals != 0.0:
+    minus_one = '' if add_endpoint else ' - 1'
+    raise ValueError(
+        'For upsampling, the target the number of timesteps must be divisible '
+        'by the number of input frames{}. (timesteps:{}, frames:{}, '
+        'add_endpoint={}).'.format(minus_one, n_timesteps, n_frames, add_endpoint))
+  return _resample_3d(inputs, n_timesteps, 'window', add_endpoint)
+
+
+def resample(inputs, n_timesteps: int, method: Text = 'linear',
+             add_endpoint: bool = True):
+  """core.resample (core.py:573-642) for 1-D / 2-D / 3-D inputs."""
+  shape = _shape(inputs)
+  if method not in ('nearest', 'linear', 'cubic', 'window'):
+    raise ValueError('Method ({}) is invalid. Must be one of {}.'.format(
+        method, "['nearest', 'linear', 'cubic', 'window']"))
+  if method == 'cubic':
+    raise NotImplementedError("'cubic' resampling is not built.")
+  if len(shape) not in (1, 2, 3):
+    raise NotImplementedError('4-D resample is outside the decoder path.')
+  x = torch_float32(inputs)
+  if len(shape) == 1:
+    x = x[None, :, None]
+  elif len(shape) == 2:
+    x = x[:, :, None]
+  if method == 'window':
+    out = upsample_with_windows(x, n_timesteps, add_endpoint)
+  else:
+    out = _resample_3d(x, n_timesteps, method, add_endpoint)
+  if len(shape) == 1:
+    out = out[0, :, 0]
+  elif len(shape) == 2:
+    out = out[:, :, 0]
+  return out
+
+
+# ----------------------------------------------------------------------------
 # Harmonic synthesis (core.py:1048-1111)
 # ----------------------------------------------------------------------------
 def harmonic_controls(amplitudes, harmonic_distribution, f0_hz, sample_rate,
@@ -224,6 +289,58 @@ def harmonic_synthesis(frequencies,
       _ptr(out), b, f, k, n_samples, float(sample_rate),
       AMP_METHODS[amp_resample_method], mode, int(bool(accumulate)), _stream()))
   return out
+
+
+def streaming_harmonic_synthesis(frequencies,
+                                 amplitudes,
+                                 harmonic_distribution=None,
+                                 initial_phase=None,
+                                 n_samples: int = 64000,
+                                 sample_rate: int = 16000,
+                                 amp_resample_method: Text = 'linear'):
+  """core.streaming_harmonic_synthesis (core.py:1114-1164): single-f0 harmonic
+  bank with a carried phase.  Returns (audio [B, n_samples], final_phase
+  [B, 1, 1]) - feed final_phase back as initial_phase for the next hop
+  (training/inference.py:463-478)."""
+  sf, sa = _shape(frequencies), _shape(amplitudes)
+  if len(sf) != 3 or len(sa) != 3 or sa != sf or sf[2] != 1:
+    raise ValueError(f'frequencies {sf} and amplitudes {sa} must both be '
+                     '[batch, n_frames, 1].')
+  if amp_resample_method not in ('nearest', 'linear', 'cubic', 'window'):
+    raise ValueError('Method ({}) is invalid. Must be one of {}.'.format(
+        amp_resample_method, "['nearest', 'linear', 'cubic', 'window']"))
+  if amp_resample_method not in AMP_METHODS:
+    raise NotImplementedError(amp_resample_method)
+  b, f, _ = sf
+  n_samples = int(n_samples)
+  if n_samples % f != 0:
+    raise NotImplementedError(
+        f'n_samples ({n_samples}) must be a multiple of the number of frames ({f}).')
+  frequencies = torch_float32(frequencies)
+  amplitudes = torch_float32(amplitudes)
+  k = 1
+  hd = None
+  lib = _lib.load()
+  if harmonic_distribution is not None:
+    hd = torch_float32(harmonic_distribution)
+    k = int(hd.shape[-1])
+    # normalize_harmonics (core.py:1143-1146): Nyquist mask + row normalisation
+    hd_n = torch.empty_like(hd)
+    amp_copy = torch.empty_like(amplitudes)
+    _lib.check(lib.ddsp_b200_harmonic_controls(
+        _ptr(amplitudes), _ptr(hd), _ptr(frequencies), _ptr(amp_copy), _ptr(hd_n),
+        b, f, k, float(sample_rate), _lib.CTL_NYQUIST, _stream()))
+    hd = hd_n
+  init = None
+  if initial_phase is not None:
+    init = torch_float32(initial_phase).reshape(b).contiguous()
+  audio = torch.empty((b, n_samples), dtype=torch.float32, device=frequencies.device)
+  final_phase = torch.empty((b,), dtype=torch.float32, device=frequencies.device)
+  _lib.check(lib.ddsp_b200_streaming_harmonic_forward(
+      _ptr(frequencies), _ptr(amplitudes), _ptr(hd), _ptr(init), _ptr(audio),
+      _ptr(final_phase), b, f, k, n_samples, float(sample_rate),
+      AMP_METHODS[amp_resample_method], _stream()))
+  return audio, final_phase.reshape(b, 1, 1)
 
 
 # ----------------------------------------------------------------------------

@@ -126,6 +126,7 @@ int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
   p.amp_method = amp_method;
   p.accumulate = accumulate;
   p.ctl_flags = 0;
+  p.init_phase = nullptr; p.final_phase = nullptr; p.mask_nyquist = 1;
   cudaStream_t st = (cudaStream_t)stream;
 
   if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_fast_supported(p)) {
@@ -157,6 +158,51 @@ int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
     harmonic_generic_kernel<0><<<grid, kHarmThreads, smem, st>>>(p);
   }
   DDSP_CHECK_LAUNCH("harmonic_forward");
+  return 0;
+}
+
+int ddsp_b200_streaming_harmonic_forward(const float* f0_hz, const float* amps,
+                                         const float* hd, const float* initial_phase,
+                                         float* audio, float* final_phase, int B,
+                                         int F, int K, int N, float sample_rate,
+                                         int amp_method, void* stream) {
+  DDSP_REQUIRE(f0_hz && amps && audio, DDSP_B200_E_INVALID,
+               "streaming_harmonic_forward: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && K >= 1 && N >= 1, DDSP_B200_E_INVALID,
+               "streaming_harmonic_forward: bad shape B=%d F=%d K=%d N=%d", B, F, K, N);
+  DDSP_REQUIRE(hd != nullptr || K == 1, DDSP_B200_E_INVALID,
+               "streaming_harmonic_forward: harmonic_distribution is NULL but K=%d", K);
+  DDSP_REQUIRE(amp_method == DDSP_B200_AMP_WINDOW ||
+                   amp_method == DDSP_B200_AMP_LINEAR,
+               DDSP_B200_E_INVALID, "streaming_harmonic_forward: bad amp_method %d",
+               amp_method);
+  DDSP_REQUIRE(N % F == 0, DDSP_B200_E_INVALID,
+               "streaming_harmonic_forward: n_samples (%d) must be divisible by "
+               "the number of frames (%d)", N, F);
+  DDSP_REQUIRE(sample_rate > 0.f, DDSP_B200_E_INVALID,
+               "streaming_harmonic_forward: sample_rate must be positive");
+  if (B == 0) return 0;
+  DDSP_REQUIRE(B <= 65535, DDSP_B200_E_INVALID,
+               "streaming_harmonic_forward: B=%d exceeds the 65535 grid limit", B);
+  HarmonicParams p;
+  p.f0 = f0_hz; p.amps = amps; p.hd = hd; p.audio = audio;
+  p.B = B; p.F = F; p.K = K; p.N = N; p.hop = N / F;
+  p.sample_rate = sample_rate; p.nyquist = sample_rate * 0.5f;
+  p.inv_sr = 1.0 / (double)sample_rate;
+  p.amp_method = amp_method; p.accumulate = 0; p.ctl_flags = 0;
+  p.init_phase = initial_phase; p.final_phase = final_phase; p.mask_nyquist = 0;
+  p.Kp = (K + 3) & ~3;
+  int FT = std::max(1, std::min(F, 2048 / p.hop));
+  while (FT > 1 && harm_smem_bytes(FT, p.Kp) > kMaxDynSmem) FT = (FT + 1) / 2;
+  DDSP_REQUIRE(harm_smem_bytes(FT, p.Kp) <= kMaxDynSmem, DDSP_B200_E_UNSUPPORTED,
+               "streaming_harmonic_forward: K=%d needs too much shared memory", K);
+  p.FT = FT;
+  const size_t smem = harm_smem_bytes(FT, p.Kp);
+  int rc = set_smem(harmonic_generic_kernel<0>, smem, "streaming_harmonic_forward");
+  if (rc) return rc;
+  dim3 grid((F + FT - 1) / FT, B);
+  harmonic_generic_kernel<0><<<grid, kHarmThreads, smem, (cudaStream_t)stream>>>(p);
+  DDSP_CHECK_LAUNCH("streaming_harmonic_forward");
   return 0;
 }
 
@@ -348,6 +394,7 @@ int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
   p.amp_method = amp_method;
   p.accumulate = 0;
   p.ctl_flags = harmonic_flags;
+  p.init_phase = nullptr; p.final_phase = nullptr; p.mask_nyquist = 1;
   // The single-pass pipeline exists for the decoder regime only; everything
   // else goes through get_controls + the two *_forward calls.
   DDSP_REQUIRE(N % F == 0 && B <= 65535 && harmonic_fast_supported(p) &&
@@ -388,6 +435,7 @@ int ddsp_b200_harmonic_backward(const float* f0_hz, const float* grad_audio,
   p.sample_rate = sample_rate; p.nyquist = sample_rate * 0.5f;
   p.inv_sr = 1.0 / (double)sample_rate;
   p.amp_method = amp_method; p.accumulate = 0; p.ctl_flags = 0; p.Kp = K;
+  p.init_phase = nullptr; p.final_phase = nullptr; p.mask_nyquist = 1;
   DDSP_REQUIRE(p.hop % 64 == 0 && p.hop <= 8192 && B <= 65535,
                DDSP_B200_E_UNSUPPORTED,
                "harmonic_backward: needs hop %% 64 == 0 (hop = %d)", p.hop);
@@ -451,6 +499,34 @@ int ddsp_b200_filtered_noise_backward(const float* grad_audio, const float* nois
   const int grid = (int)std::min<long long>(n_tiles, (long long)kNumSMs * per_sm);
   noise_backward_kernel<<<grid, kNbThreads, smem, (cudaStream_t)stream>>>(p);
   DDSP_CHECK_LAUNCH("filtered_noise_backward");
+  return 0;
+}
+
+int ddsp_b200_resample(const float* in, float* out, int B, int F, int C, int N,
+                       int method, int add_endpoint, void* stream) {
+  DDSP_REQUIRE(in && out, DDSP_B200_E_INVALID, "resample: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && C >= 1 && N >= 1, DDSP_B200_E_INVALID,
+               "resample: bad shape B=%d F=%d C=%d N=%d", B, F, C, N);
+  DDSP_REQUIRE(method >= 0 && method <= 2, DDSP_B200_E_INVALID,
+               "resample: bad method %d", method);
+  if (method == 0) {
+    // upsample_with_windows (core.py:676-693)
+    const int n_frames = add_endpoint ? F + 1 : F;
+    const int n_intervals = n_frames - 1;
+    DDSP_REQUIRE(n_frames < N, DDSP_B200_E_INVALID,
+                 "Upsample with windows cannot be used for downsampling"
+                 "More input frames (%d) than output timesteps (%d)", n_frames, N);
+    DDSP_REQUIRE(n_intervals > 0 && N % n_intervals == 0, DDSP_B200_E_INVALID,
+                 "For upsampling, the target the number of timesteps must be "
+                 "divisible by the number of input frames%s. (timesteps:%d, "
+                 "frames:%d, add_endpoint=%s).", add_endpoint ? "" : " - 1", N,
+                 n_frames, add_endpoint ? "True" : "False");
+  }
+  if (B == 0) return 0;
+  const int64_t total = (int64_t)B * N * C;
+  resample_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      in, out, B, F, C, N, method, add_endpoint);
+  DDSP_CHECK_LAUNCH("resample");
   return 0;
 }
 

@@ -60,6 +60,49 @@ add_kernel(const float* a, const float* b, float* out, int64_t n) {
   for (; i < n; i += stride) out[i] = a[i] + b[i];
 }
 
+// core.resample / core.upsample_with_windows (core.py:573-714) as a stand-alone
+// op: [B, F, C] -> [B, N, C].  method 0 = 'window' (Hann overlap-add ==
+// two-tap raised cosine), 1 = 'linear' (tf v1 bilinear,
+// align_corners = !add_endpoint), 2 = 'nearest'.  Index math follows TF's
+// float32 scale * index for linear / nearest; the window method needs an integer
+// hop (checked by the caller, core.py:687-693).
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int F,
+                int C, int N, int method, int add_endpoint) {
+  const int64_t total = (int64_t)B * N * C;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float scale = (!add_endpoint && N > 1) ? (float)(F - 1) / (float)(N - 1)
+                                               : (float)F / (float)N;
+  const int hop = add_endpoint ? N / max(F, 1) : N / max(F - 1, 1);
+  for (; idx < total; idx += stride) {
+    const int c = (int)(idx % C);
+    const int64_t bt = idx / C;
+    const int t = (int)(bt % N);
+    const int b = (int)(bt / N);
+    const float* x = in + (size_t)b * F * C + c;
+    float v;
+    if (method == 0) {
+      const int i = t / hop, r = t - i * hop;
+      const int i1 = min(i + 1, F - 1);            // add_endpoint: frame F := F-1
+      const float w1 = 0.5f - 0.5f * cospif((float)r / (float)hop);
+      v = x[(size_t)i * C] * (1.0f - w1) + x[(size_t)i1 * C] * w1;
+    } else if (method == 1) {
+      const float src = (float)t * scale;
+      const float fl = floorf(src);
+      const int lo = max((int)fl, 0);
+      const int hi = min((int)ceilf(src), F - 1);
+      const float top = x[(size_t)min(lo, F - 1) * C], bot = x[(size_t)hi * C];
+      v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), src - fl));
+    } else {
+      const float src = (float)t * scale;
+      const int i = min((int)(add_endpoint ? floorf(src) : roundf(src)), F - 1);
+      v = x[(size_t)i * C];
+    }
+    out[idx] = v;
+  }
+}
+
 // tf.random.uniform([B, N], -1, 1) stand-in (synths.py:192-193): Philox4x32-10.
 __global__ void __launch_bounds__(256)
 uniform_noise_kernel(float* __restrict__ out, int B, int N, uint64_t seed,

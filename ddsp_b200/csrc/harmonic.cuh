@@ -36,6 +36,10 @@ struct HarmonicParams {
   // DDSP_B200_CTL_*: they are raw network outputs; Harmonic.get_controls
   // (synths.py:94-121) is applied while the frame slab is staged (fast path).
   int ctl_flags;
+  // Streaming synthesis (core.harmonic_oscillator_bank, core.py:966-1025):
+  const float* init_phase;   // [B] radians added to the phase, or nullptr
+  float* final_phase;        // [B] phase after the last sample (radians), or nullptr
+  int mask_nyquist;          // 0: no audio-rate Nyquist mask (streaming bank has none)
 };
 
 // The reference's float32 evaluation of the k-th harmonic's audio-rate
@@ -134,6 +138,9 @@ harmonic_generic_kernel(HarmonicParams p) {
   if (tid == 0) {
     unsigned long long P = 0;
     for (int w = 0; w < kHarmThreads / 32; ++w) P += sRed[w];
+    const double init_rad = p.init_phase ? (double)p.init_phase[b] : 0.0;
+    const unsigned long long Pinit = turns_to_fix64(init_rad * 0.15915494309189535);
+    P += Pinit;
     for (int j = 0; j < nfr; ++j) {
       double a0 = (double)sF0[j] * p.inv_sr;
       double a1 = (double)sF0[j + 1] * p.inv_sr;
@@ -141,6 +148,12 @@ harmonic_generic_kernel(HarmonicParams p) {
       sA[j] = turns_to_fix64(a0);
       sD[j] = turns_to_fix64((a1 - a0) / (double)hop);
       P += turns_to_fix64((double)hop * a0 + (a1 - a0) * (0.5 * (hop - 1)));
+    }
+    if (p.final_phase != nullptr && i0 + nfr == F) {
+      // angular_cumsum's last value in [0, 2 pi) plus the initial phase
+      // (core.py:1004-1012): final_phase = phases[:, -1]
+      const double turns = (double)(P - Pinit) * 5.421010862427522e-20;   // 2^-64
+      p.final_phase[b] = (float)(turns * 6.283185307179586 + init_rad);
     }
   }
   __syncthreads();
@@ -174,8 +187,9 @@ harmonic_generic_kernel(HarmonicParams p) {
     const float* x1 = x0 + Kp;
 
     // live harmonic count (Nyquist mask of oscillator_bank, core.py:942)
-    const bool monotone = (f_lo >= 1.0f) && (f_hi >= 1.0f);
-    int klive = monotone ? live_harmonics(f_lo, f_hi, frac, K, p.nyquist) : K;
+    const bool monotone = !p.mask_nyquist || ((f_lo >= 1.0f) && (f_hi >= 1.0f));
+    int klive = (p.mask_nyquist && monotone)
+                    ? live_harmonics(f_lo, f_hi, frac, K, p.nyquist) : K;
 
     float acc = 0.f;
     if (MODE == 1 || !monotone) {

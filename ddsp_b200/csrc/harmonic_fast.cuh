@@ -17,6 +17,8 @@
 //     harmonics below the warp-wide minimum run unmasked, the few between
 //     min and max run with a per-lane predicate.
 #pragma once
+#include <cmath>
+
 #include "harmonic.cuh"
 
 namespace ddsp {
@@ -448,6 +450,19 @@ inline int launch_harmonic_fast(HarmonicParams p, cudaStream_t st) {
   int ft_fill = (int)std::max<long long>(1, ((long long)p.B * p.F + want_ctas - 1) / want_ctas);
   FT = std::min(FT, std::max(ft_fill, std::min(8, p.F)));
   FT = std::min(FT, p.F);
+  {
+    // Wave quantisation: with ~3 resident CTAs per SM a grid of a few waves can
+    // leave a third of the chip idle in the last one.  Halve the tile (at most
+    // twice) when that buys more than 8 % of wave efficiency.
+    const double slots = 3.0 * kNumSMs;
+    auto eff = [&](int ft) {
+      const double n = (double)p.B * ((p.F + ft - 1) / ft);
+      return n / (std::ceil(n / slots) * slots);
+    };
+    for (int tries = 0; tries < 2 && FT >= 16; ++tries) {
+      if (eff(FT / 2) > eff(FT) + 0.08) FT /= 2; else break;
+    }
+  }
   while (FT > 1 && fast_smem_layout(FT, p.Kp, p.hop).total > 100 * 1024) FT = (FT + 1) / 2;
   const size_t smem = fast_smem_layout(FT, p.Kp, p.hop).total;
   if (smem > 200 * 1024) return 1;

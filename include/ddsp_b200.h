@@ -89,6 +89,20 @@ int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
                                int K, int N, float sample_rate, int amp_method,
                                int phase_mode, int accumulate, void* stream);
 
+/* core.streaming_harmonic_synthesis after its normalize_harmonics call =
+ * resample f0 ('linear') and amplitudes (amp_method) + harmonic_oscillator_bank
+ * (core.py:1151-1163, 966-1025): phase = cumsum(omega) + initial_phase, harmonic
+ * k uses k * phase, NO audio-rate Nyquist mask, and the phase after the last
+ * sample is returned (wrapped cumsum in [0, 2 pi) + initial_phase, as
+ * angular_cumsum gives).  hd must already be normalize_harmonics'ed
+ * (ddsp_b200_harmonic_controls with DDSP_B200_CTL_NYQUIST only).
+ * initial_phase [B] radians or NULL; final_phase [B] or NULL. */
+int ddsp_b200_streaming_harmonic_forward(const float* f0_hz, const float* amps,
+                                         const float* hd, const float* initial_phase,
+                                         float* audio, float* final_phase, int B,
+                                         int F, int K, int N, float sample_rate,
+                                         int amp_method, void* stream);
+
 /* FilteredNoise.get_controls (synths.py:165-179): exp_sigmoid(x + bias). */
 int ddsp_b200_noise_controls(const float* mag_in, float* mag_out, int64_t n,
                              float initial_bias, int apply_scale, void* stream);
@@ -167,6 +181,12 @@ int ddsp_b200_filtered_noise_backward(const float* grad_audio, const float* nois
                                       uint64_t seed, uint64_t offset, float* dmags,
                                       int B, int F, int nb, int N, int window_size,
                                       void* stream);
+
+/* core.resample / core.upsample_with_windows (core.py:573-714) stand-alone:
+ * in [B,F,C] -> out [B,N,C].  method: 0 'window', 1 'linear', 2 'nearest'
+ * ('cubic' is not built).  add_endpoint as in the reference. */
+int ddsp_b200_resample(const float* in, float* out, int B, int F, int C, int N,
+                       int method, int add_endpoint, void* stream);
 
 /* processors.Add.get_signal (processors.py:174-176). out may alias a or b. */
 int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,

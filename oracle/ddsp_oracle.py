@@ -365,6 +365,47 @@ def harmonic_synthesis(frequencies, amplitudes, harmonic_shifts=None,
                          nyquist_mask=mask)
 
 
+def harmonic_oscillator_bank(frequency, amplitude_envelopes, initial_phase=None,
+                             sample_rate=16000, use_angular_cumsum=True,
+                             dtype=np.float64):
+  """core.py:966-1025."""
+  frequency = _as(frequency, dtype)
+  ae = _as(amplitude_envelopes, dtype)
+  omega = (frequency * np.asarray(TWO_PI, dtype)).astype(dtype)
+  omega = (omega / np.asarray(float(sample_rate), dtype)).astype(dtype)
+  if use_angular_cumsum:
+    phases = angular_cumsum(omega, dtype=dtype)
+  else:
+    phases = _cumsum_sequential(omega, 1, dtype)
+  if initial_phase is None:
+    initial_phase = np.zeros([phases.shape[0], 1, 1], dtype)
+  phases = (phases + _as(initial_phase, dtype)).astype(dtype)
+  final_phase = phases[:, -1:, 0:1]
+  n_harmonics = int(ae.shape[-1])
+  f_ratios = np.linspace(1.0, float(n_harmonics), n_harmonics).astype(dtype)
+  phases = (phases * f_ratios[None, None, :]).astype(dtype)
+  audio = np.sum((ae * np.sin(phases)).astype(dtype), axis=-1, dtype=dtype)
+  return audio, final_phase
+
+
+def streaming_harmonic_synthesis(frequencies, amplitudes,
+                                 harmonic_distribution=None, initial_phase=None,
+                                 n_samples=64000, sample_rate=16000,
+                                 amp_resample_method='linear', dtype=np.float64):
+  """core.py:1114-1164."""
+  frequencies = _as(frequencies, dtype)
+  amplitudes = _as(amplitudes, dtype)
+  if harmonic_distribution is not None:
+    hd = normalize_harmonics(_as(harmonic_distribution, dtype), frequencies,
+                             sample_rate, dtype)
+    ha = (amplitudes * hd).astype(dtype)
+  else:
+    ha = amplitudes
+  fe = resample(frequencies, n_samples, dtype=dtype)
+  ae = resample(ha, n_samples, method=amp_resample_method, dtype=dtype)
+  return harmonic_oscillator_bank(fe, ae, initial_phase, sample_rate, dtype=dtype)
+
+
 # ----------------------------------------------------------------------------
 # Time-varying FIR / filtered noise (core.py:1316-1655)
 # ----------------------------------------------------------------------------

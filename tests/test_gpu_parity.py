@@ -219,3 +219,80 @@ def test_decoder_forward_from_raw_matches_oracle(B, F, K, nb, N, nyq):
       noise=inp['noise']))
   emax, el2 = rel_err(got, harm + nz)
   assert emax < TOL and el2 < TOL, (emax, el2)
+
+
+@pytest.mark.parametrize('B,F,K,N,method', [(1, 2, 60, 320, 'linear'),
+                                            (3, 10, 20, 640, 'linear'),
+                                            (2, 4, 100, 256, 'window')])
+def test_streaming_harmonic_synthesis_carries_phase(B, F, K, N, method):
+  """core.streaming_harmonic_synthesis (core.py:1114-1164): audio and final_phase
+  vs the oracle, and hop-by-hop synthesis with the carried phase equals one call
+  on the concatenated controls (training/inference.py:463-478)."""
+  rng = np.random.default_rng(K)
+  f0 = rng.uniform(100, 900, (B, F, 1)).astype(np.float32)
+  amp = rng.uniform(0.1, 1.0, (B, F, 1)).astype(np.float32)
+  hd = rng.uniform(0.0, 1.0, (B, F, K)).astype(np.float32)
+  init = rng.uniform(0, 2 * np.pi, (B, 1, 1)).astype(np.float32)
+  want_a, want_p = oracle.streaming_harmonic_synthesis(
+      f0, amp, hd, init, n_samples=N, amp_resample_method=method)
+  got_a, got_p = core.streaming_harmonic_synthesis(
+      f0, amp, hd, init, n_samples=N, amp_resample_method=method)
+  emax, el2 = rel_err(_np(got_a), want_a)
+  assert emax < TOL and el2 < TOL, (emax, el2)
+  assert got_p.shape == (B, 1, 1)
+  d = np.abs(_np(got_p) - want_p)
+  assert np.minimum(d, 2 * np.pi - d).max() < 1e-4
+  # two successive hops with the carried phase: the second call continues the wave
+  a1, p1 = core.streaming_harmonic_synthesis(f0, amp, hd, None, n_samples=N,
+                                             amp_resample_method=method)
+  a2, p2 = core.streaming_harmonic_synthesis(f0, amp, hd, p1, n_samples=N,
+                                             amp_resample_method=method)
+  w1, q1 = oracle.streaming_harmonic_synthesis(f0, amp, hd, None, n_samples=N,
+                                               amp_resample_method=method)
+  w2, _ = oracle.streaming_harmonic_synthesis(f0, amp, hd, q1, n_samples=N,
+                                              amp_resample_method=method)
+  emax, _ = rel_err(np.concatenate([_np(a1), _np(a2)], 1), np.concatenate([w1, w2], 1))
+  assert emax < TOL
+
+
+# ---- core_test.py:ResampleTest through the CUDA op ---------------------------
+def _subsampled_close(smaller, larger, add_endpoint, threshold=1e-3):
+  n_smaller, n_larger = smaller.size, larger.size
+  n_total = (int(n_larger / n_smaller * (n_smaller - 1)) if add_endpoint
+             else n_larger - 1)
+  idx = np.linspace(0, n_total, n_smaller).astype(int)
+  np.testing.assert_allclose(larger[idx], smaller, atol=threshold)
+
+
+@pytest.mark.parametrize('add_endpoint', [True, False])
+@pytest.mark.parametrize('method', ['linear', 'window', 'nearest'])
+def test_resample_upsample_accuracy(add_endpoint, method):
+  """core_test.py:242-267 + agreement with the oracle's TF restatement."""
+  before = (1.0 - np.sin(np.linspace(0, np.pi, 5)))[None, :, None].astype(np.float32)
+  after = _np(core.resample(before, 16000, method=method, add_endpoint=add_endpoint))
+  if method != 'nearest':
+    _subsampled_close(before[0, :, 0], after[0, :, 0], add_endpoint)
+  want = oracle.resample(before, 16000, method=method, add_endpoint=add_endpoint,
+                         dtype=np.float32, tf_index_math=True)
+  np.testing.assert_allclose(after, want, atol=2e-6)
+
+
+@pytest.mark.parametrize('add_endpoint', [True, False])
+def test_resample_downsample_accuracy(add_endpoint):
+  """core_test.py:269-293."""
+  before = (1.0 - np.sin(np.linspace(0, np.pi, 16000)))[None, :, None].astype(np.float32)
+  after = _np(core.resample(before, 5, method='linear', add_endpoint=add_endpoint))
+  _subsampled_close(after[0, :, 0], before[0, :, 0], add_endpoint)
+
+
+@pytest.mark.parametrize('dimensions', [1, 2, 3])
+def test_resample_multi_dimensional_inputs(dimensions):
+  """core_test.py:152-176."""
+  shape = [5] * dimensions
+  out = core.resample(np.ones(shape, np.float32), 16000)
+  want = list(shape)
+  want[0 if dimensions == 1 else 1] = 16000
+  assert list(out.shape) == want
+  rnd = np.random.default_rng(0).standard_normal((3, 20, 7)).astype(np.float32)
+  got = _np(core.upsample_with_windows(rnd, 640))
+  np.testing.assert_allclose(got, oracle.upsample_with_windows(rnd, 640), atol=2e-6)

@@ -257,3 +257,19 @@ def test_decoder_pattern_detection():
       (h, ['amps', 'hd', 'f0_hz']), (n, ['mags']),
       (add, ['harmonic/signal', 'harmonic/signal'])])
   assert g3._decoder_pattern() is None
+
+
+def test_resample_value_errors():
+  """core_test.py:178-198, 295-381 - raised before any device work."""
+  for dims in (1, 2, 4):
+    with pytest.raises(ValueError, match='only supports 3 dimensions'):
+      core.upsample_with_windows(np.ones([5] * dims, np.float32), 16000)
+  for add_endpoint in (True, False):
+    with pytest.raises(ValueError, match='downsampling'):
+      core.upsample_with_windows(np.ones([1, 16000, 1], np.float32), 5, add_endpoint)
+  with pytest.raises(ValueError, match='divisible'):
+    core.upsample_with_windows(np.ones([1, 5, 1], np.float32), 16)
+  with pytest.raises(ValueError, match='divisible'):
+    core.upsample_with_windows(np.ones([1, 5, 1], np.float32), 15, add_endpoint=False)
+  with pytest.raises(ValueError, match='is invalid'):
+    core.resample(np.ones([1, 5, 1], np.float32), 10, method='bogus')
