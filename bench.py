@@ -118,11 +118,11 @@ def make_host_inputs(batch, seed):
 # reference arm: the CPU port of the reference decoder, host cores only
 # ----------------------------------------------------------------------------
 def cpu_reference_throughput(items, repeats=1, threads=None):
-  """samples/s of oracle/ref_port_torch.decoder on `items` batch items."""
+  """samples/s of oracle/ref_port_torch.decoder on `items` batch items, on all
+  the host threads available (torchrun exports OMP_NUM_THREADS=1; undo that)."""
   import torch
   from oracle import ref_port_torch as rp
-  if threads:
-    torch.set_num_threads(threads)
+  torch.set_num_threads(threads or os.cpu_count() or 1)
   inp = make_host_inputs(items, seed=99)
   t = {k: torch.from_numpy(v) for k, v in inp.items()}
   best = None
@@ -139,7 +139,7 @@ def cpu_reference_throughput(items, repeats=1, threads=None):
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
-    return  # other ranks exit 0 without work
+    return None  # other ranks exit 0 without work
   import torch
   cores = torch.get_num_threads()
   items = 8  # bounded sample of the B=32 workload: 8 items per step
@@ -168,7 +168,7 @@ def run_reference(args):
               'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
-  print(json.dumps(line), flush=True)
+  return line
 
 
 # ----------------------------------------------------------------------------
@@ -340,7 +340,7 @@ def run_ours(args):
     if world > 1:
       dist.barrier()
       dist.destroy_process_group()
-    return
+    return None
 
   peak, peak_src = _measured_peaks()
   dom_is_harm = ms_harm >= ms_noise
@@ -392,13 +392,30 @@ def run_ours(args):
       'cpu_baseline': cpu,
   }
   line.update(extra)
-  print(json.dumps(line), flush=True)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
+  return line
 
 
 def main():
+  # Keep stdout clean for the ONE JSON line: NCCL (and anything else native)
+  # writes its banners to fd 1, so run with fd 1 pointed at stderr and restore
+  # it only for the final print.
+  sys.stdout.flush()
+  saved_stdout = os.dup(1)
+  os.dup2(2, 1)
+  try:
+    line = _main()
+  finally:
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+  if line is not None:
+    print(json.dumps(line), flush=True)
+
+
+def _main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=50)
@@ -412,9 +429,8 @@ def main():
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
   if args.impl == 'reference':
-    run_reference(args)
-  else:
-    run_ours(args)
+    return run_reference(args)
+  return run_ours(args)
 
 
 if __name__ == '__main__':

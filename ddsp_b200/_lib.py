@@ -62,6 +62,9 @@ SIGNATURES = {
         (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'ddsp_b200_filtered_noise_backward':
         (_i, [_vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _vp]),
+    'ddsp_b200_oscillator_bank_workspace': (_sz, [_i, _i, _i]),
+    'ddsp_b200_oscillator_bank':
+        (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
     'ddsp_b200_resample': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'ddsp_b200_add': (_i, [_vp, _vp, _vp, _i64, _vp]),
 }

@@ -211,6 +211,71 @@ def harmonic_controls(amplitudes, harmonic_distribution, f0_hz, sample_rate,
   return amps_out, hd_out
 
 
+def safe_divide(numerator, denominator, eps=1e-7):
+  """core.safe_divide (core.py:207-210)."""
+  safe = torch.where(denominator == 0.0, torch.full_like(denominator, eps),
+                     denominator)
+  return numerator / safe
+
+
+def get_harmonic_frequencies(frequencies, n_harmonics: int):
+  """core.get_harmonic_frequencies (core.py:1028-1045): f0 * [1..K]."""
+  frequencies = torch_float32(frequencies)
+  ratios = torch.linspace(1.0, float(n_harmonics), int(n_harmonics),
+                          device=frequencies.device)
+  return frequencies * ratios[None, None, :]
+
+
+def remove_above_nyquist(frequency_envelopes, amplitude_envelopes,
+                         sample_rate: int = 16000):
+  """core.remove_above_nyquist (core.py:869-891)."""
+  frequency_envelopes = torch_float32(frequency_envelopes)
+  amplitude_envelopes = torch_float32(amplitude_envelopes)
+  return torch.where(frequency_envelopes >= sample_rate / 2.0,
+                     torch.zeros_like(amplitude_envelopes), amplitude_envelopes)
+
+
+def normalize_harmonics(harmonic_distribution, f0_hz=None, sample_rate=None):
+  """core.normalize_harmonics (core.py:894-907) on the controls kernel."""
+  sh = _shape(harmonic_distribution)
+  if len(sh) != 3:
+    raise ValueError(f'harmonic_distribution must be 3-D, got {sh}.')
+  b, f, _ = sh
+  mask = sample_rate is not None and f0_hz is not None
+  if f0_hz is None:
+    f0_hz = torch.zeros((b, f, 1), dtype=torch.float32, device=_device())
+  amps = torch.zeros((b, f, 1), dtype=torch.float32, device=_device())
+  _, hd = harmonic_controls(amps, harmonic_distribution, f0_hz,
+                            sample_rate if mask else 2.0, scale=False,
+                            normalize_below_nyquist=mask)
+  return hd
+
+
+def oscillator_bank(frequency_envelopes, amplitude_envelopes,
+                    sample_rate: int = 16000, sum_sinusoids: bool = True,
+                    use_angular_cumsum: bool = False):
+  """core.oscillator_bank (core.py:911-962) on audio-rate envelopes
+  [batch, n_samples, n_sinusoids].  Phase is accumulated exactly (wrapped,
+  64-bit fixed point) whatever `use_angular_cumsum` says."""
+  del use_angular_cumsum
+  sf, sa = _shape(frequency_envelopes), _shape(amplitude_envelopes)
+  if len(sf) != 3 or sf != sa:
+    raise ValueError(f'frequency_envelopes {sf} and amplitude_envelopes {sa} must '
+                     'both be [batch, n_samples, n_sinusoids].')
+  b, n, k = sf
+  f = torch_float32(frequency_envelopes)
+  a = torch_float32(amplitude_envelopes)
+  lib = _lib.load()
+  out = torch.empty((b, n) if sum_sinusoids else (b, n, k), dtype=torch.float32,
+                    device=f.device)
+  nbytes = lib.ddsp_b200_oscillator_bank_workspace(b, n, k)
+  ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=f.device)
+  _lib.check(lib.ddsp_b200_oscillator_bank(
+      _ptr(f), _ptr(a), _ptr(out), b, n, k, float(sample_rate),
+      int(bool(sum_sinusoids)), _ptr(ws), nbytes, _stream()))
+  return out
+
+
 def harmonic_synthesis(frequencies,
                        amplitudes,
                        harmonic_shifts=None,

@@ -14,6 +14,7 @@
 #include "noise_fused.cuh"
 #include "noise_pipe.cuh"
 #include "backward.cuh"
+#include "oscbank.cuh"
 
 namespace ddsp {
 
@@ -499,6 +500,55 @@ int ddsp_b200_filtered_noise_backward(const float* grad_audio, const float* nois
   const int grid = (int)std::min<long long>(n_tiles, (long long)kNumSMs * per_sm);
   noise_backward_kernel<<<grid, kNbThreads, smem, (cudaStream_t)stream>>>(p);
   DDSP_CHECK_LAUNCH("filtered_noise_backward");
+  return 0;
+}
+
+size_t ddsp_b200_oscillator_bank_workspace(int B, int N, int K) {
+  if (B <= 0 || N <= 0 || K <= 0) return 0;
+  const size_t n_chunks = ((size_t)N + kObChunk - 1) / kObChunk;
+  return sizeof(unsigned long long) * (size_t)B * n_chunks * K + 256;
+}
+
+int ddsp_b200_oscillator_bank(const float* frequency_envelopes,
+                              const float* amplitude_envelopes, float* out, int B,
+                              int N, int K, float sample_rate, int sum_sinusoids,
+                              void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  DDSP_REQUIRE(frequency_envelopes && amplitude_envelopes && out,
+               DDSP_B200_E_INVALID, "oscillator_bank: null pointer");
+  DDSP_REQUIRE(B >= 0 && N >= 1 && K >= 1, DDSP_B200_E_INVALID,
+               "oscillator_bank: bad shape B=%d N=%d K=%d", B, N, K);
+  DDSP_REQUIRE(sample_rate > 0.f, DDSP_B200_E_INVALID,
+               "oscillator_bank: sample_rate must be positive");
+  if (B == 0) return 0;
+  DDSP_REQUIRE(B <= 65535, DDSP_B200_E_INVALID,
+               "oscillator_bank: B=%d exceeds the 65535 grid limit", B);
+  const size_t need = ddsp_b200_oscillator_bank_workspace(B, N, K);
+  DDSP_REQUIRE(workspace != nullptr && workspace_bytes >= need, DDSP_B200_E_WORKSPACE,
+               "oscillator_bank: workspace of %zu B needed, %zu given", need,
+               workspace_bytes);
+  unsigned long long* sums = reinterpret_cast<unsigned long long*>(
+      ((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const int n_chunks = (N + kObChunk - 1) / kObChunk;
+  const double inv_sr = 1.0 / (double)sample_rate;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(n_chunks, B);
+  oscbank_chunk_sums<<<grid, kObThreads, 0, st>>>(frequency_envelopes, sums, N, K,
+                                                 n_chunks, inv_sr);
+  DDSP_CHECK_LAUNCH("oscillator_bank(chunk sums)");
+  const int64_t BK = (int64_t)B * K;
+  oscbank_scan_chunks<<<(int)((BK + kObThreads - 1) / kObThreads), kObThreads, 0, st>>>(
+      sums, K, n_chunks, BK);
+  DDSP_CHECK_LAUNCH("oscillator_bank(scan)");
+  if (sum_sinusoids)
+    oscbank_apply<true><<<grid, kObThreads, 0, st>>>(
+        frequency_envelopes, amplitude_envelopes, sums, out, N, K, n_chunks, inv_sr,
+        sample_rate * 0.5f);
+  else
+    oscbank_apply<false><<<grid, kObThreads, 0, st>>>(
+        frequency_envelopes, amplitude_envelopes, sums, out, N, K, n_chunks, inv_sr,
+        sample_rate * 0.5f);
+  DDSP_CHECK_LAUNCH("oscillator_bank(apply)");
   return 0;
 }
 

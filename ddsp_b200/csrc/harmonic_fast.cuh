@@ -18,6 +18,7 @@
 //     min and max run with a per-lane predicate.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 
 #include "harmonic.cuh"
 
@@ -286,8 +287,8 @@ __device__ __forceinline__ void harmonic_controls_rows(
   }
 }
 
-template <bool WINDOW>
-__global__ void __launch_bounds__(kFastThreads)
+template <bool WINDOW, int NT>
+__global__ void __launch_bounds__(NT)
 harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int FT = p.FT, Kp = p.Kp, K = p.K, F = p.F, hop = p.hop;
@@ -331,27 +332,27 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   // resolution), reduced over the CTA; every CTA recomputes it from f0 (<= 4 KB
   // of L2-resident data) instead of a serial scan over time.
   double part = 0.0;
-  for (int j = tid; j < i0; j += kFastThreads) part += (double)f0b[j];
+  for (int j = tid; j < i0; j += NT) part += (double)f0b[j];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if (lane == 0) sRedD[warp] = part;
 
   // ---- 2. small tables ----
   const bool raw_scale = p.ctl_flags & DDSP_B200_CTL_SCALE;
-  for (int j = tid; j <= nfr; j += kFastThreads) {
+  for (int j = tid; j <= nfr; j += NT) {
     int g = min(i0 + j, F - 1);
     sF0[j] = f0b[g];
     const float a = ampb[g];
     sAmp[j] = raw_scale ? exp_sigmoid_f(a) : a;     // synths.py:110-111
   }
-  for (int j = tid; j < kSinTab; j += kFastThreads) {
+  for (int j = tid; j < kSinTab; j += NT) {
     float s, c;
     sincospif(2.0f * (float)j / (float)kSinTab, &s, &c);
     sTab[j] = make_float2(s, c);
   }
   {
     const float inv_hop = 1.0f / (float)hop;
-    for (int r = tid; r < hop; r += kFastThreads) {
+    for (int r = tid; r < hop; r += NT) {
       const float frac = (float)r * inv_hop;
       sW[r] = WINDOW ? (0.5f - 0.5f * cospif(frac)) : frac;
     }
@@ -359,12 +360,12 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   if (!use_tma) {
     if (p.hd != nullptr) {
       const float* hdb = p.hd + ((size_t)b * F + i0) * K;
-      for (int idx = tid; idx < rows_in * Kp; idx += kFastThreads) {
+      for (int idx = tid; idx < rows_in * Kp; idx += NT) {
         int r = idx / Kp, c = idx - r * Kp;
         sX[idx] = (c < K) ? hdb[r * K + c] : 0.f;
       }
     } else {
-      for (int idx = tid; idx < rows_in * Kp; idx += kFastThreads)
+      for (int idx = tid; idx < rows_in * Kp; idx += NT)
         sX[idx] = (idx % Kp == 0) ? 1.0f : 0.f;
     }
   }
@@ -375,7 +376,7 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
   // frames per warp pass; P_i = tile prefix + exclusive scan of the totals.
   if (warp == 0) {
     double fsum = 0.0;
-    for (int w = 0; w < kFastThreads / 32; ++w) fsum += sRedD[w];
+    for (int w = 0; w < NT / 32; ++w) fsum += sRedD[w];
     const double a_first = (double)f0b[0] * p.inv_sr;
     const double a_tile = (double)sF0[0] * p.inv_sr;
     unsigned long long P = turns_to_fix64(
@@ -400,7 +401,7 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
       P += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
-  for (int j = tid; j < nfr; j += kFastThreads) {
+  for (int j = tid; j < nfr; j += NT) {
     const float f_lo = sF0[j], f_hi = sF0[j + 1];
     if (f_lo >= 1.0f && f_hi >= 1.0f) {
       sKc[2 * j] = live_harmonics(f_lo, f_hi, 0.0f, K, p.nyquist);
@@ -417,20 +418,20 @@ harmonic_fast_kernel(HarmonicParams p, int use_tma) {
     // exp_sigmoid, frame-rate Nyquist mask on float32 f0*k, row normalisation
     // with safe_divide.  One warp per frame row, rows stay in shared memory.
     const bool nyq = p.ctl_flags & DDSP_B200_CTL_NYQUIST;
-    for (int r0 = warp * 4; r0 < rows_in; r0 += (kFastThreads / 32) * 4)
+    for (int r0 = warp * 4; r0 < rows_in; r0 += (NT / 32) * 4)
       harmonic_controls_rows(sX, sF0, r0, rows_in, K, Kp, p.nyquist, raw_scale, nyq,
                              lane);
     __syncthreads();
   }
   if (rows_in < nfr + 1) {                    // frame F := frame F-1
-    for (int c = tid; c < Kp; c += kFastThreads)
+    for (int c = tid; c < Kp; c += NT)
       sX[nfr * Kp + c] = sX[(nfr - 1) * Kp + c];
     __syncthreads();
   }
 
   // ---- 4. samples: warp w takes frames w, w+8, ...; 64 samples per pass ----
   float* outb = p.audio + (size_t)b * p.N + (size_t)i0 * hop;
-  for (int li = warp; li < nfr; li += kFastThreads / 32) {
+  for (int li = warp; li < nfr; li += NT / 32) {
     harmonic_frame_pass(sX + li * Kp, sX + (li + 1) * Kp, sP[li], sA[li], sD[li],
                         sKc[2 * li], sKc[2 * li + 1], sF0[li], sF0[li + 1],
                         sAmp[li], sAmp[li + 1], sW, sTab, K, p.nyquist, hop, lane,
@@ -445,7 +446,13 @@ inline bool harmonic_fast_supported(const HarmonicParams& p) {
 // Returns 0 on success, negative on error, 1 if it declines (caller falls back).
 inline int launch_harmonic_fast(HarmonicParams p, cudaStream_t st) {
   p.Kp = (p.K + 3) & ~3;
+  // debug / tuning knobs (not part of the ABI): threads per CTA and frames per tile
+  static const int env_nt = [] { const char* e = getenv("DDSP_B200_HARM_NT"); return e ? atoi(e) : 256; }();
+  static const int env_ft = [] { const char* e = getenv("DDSP_B200_HARM_FT"); return e ? atoi(e) : 0; }();
+  const int NT = (env_nt == 128) ? 128 : 256;
   int FT = std::max(1, 2048 / p.hop);
+  if (NT == 128) FT = std::max(1, FT / 2);
+  if (env_ft > 0) FT = std::min(FT, env_ft);
   const long long want_ctas = 4ll * kNumSMs;
   int ft_fill = (int)std::max<long long>(1, ((long long)p.B * p.F + want_ctas - 1) / want_ctas);
   FT = std::min(FT, std::max(ft_fill, std::min(8, p.F)));
@@ -474,18 +481,26 @@ inline int launch_harmonic_fast(HarmonicParams p, cudaStream_t st) {
   cudaError_t e;
   if (p.amp_method == DDSP_B200_AMP_WINDOW) {
     if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(harmonic_fast_kernel<true>,
+      e = cudaFuncSetAttribute(harmonic_fast_kernel<true, 256>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(harmonic_fast_kernel<true, 128>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return 1;
     }
-    harmonic_fast_kernel<true><<<grid, kFastThreads, smem, st>>>(p, use_tma);
+    if (NT == 128) harmonic_fast_kernel<true, 128><<<grid, 128, smem, st>>>(p, use_tma);
+    else harmonic_fast_kernel<true, 256><<<grid, 256, smem, st>>>(p, use_tma);
   } else {
     if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(harmonic_fast_kernel<false>,
+      e = cudaFuncSetAttribute(harmonic_fast_kernel<false, 256>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(harmonic_fast_kernel<false, 128>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return 1;
     }
-    harmonic_fast_kernel<false><<<grid, kFastThreads, smem, st>>>(p, use_tma);
+    if (NT == 128) harmonic_fast_kernel<false, 128><<<grid, 128, smem, st>>>(p, use_tma);
+    else harmonic_fast_kernel<false, 256><<<grid, 256, smem, st>>>(p, use_tma);
   }
   DDSP_CHECK_LAUNCH("harmonic_forward(fast)");
   return 0;

@@ -182,6 +182,17 @@ int ddsp_b200_filtered_noise_backward(const float* grad_audio, const float* nois
                                       int B, int F, int nb, int N, int window_size,
                                       void* stream);
 
+/* core.oscillator_bank (core.py:911-962) on audio-rate envelopes [B,N,K]:
+ * Nyquist mask, exact wrapped phase accumulation (three-pass chunked scan in
+ * 64-bit fixed point), amp * sin(phase), summed over k when sum_sinusoids != 0
+ * (out [B,N]) or not (out [B,N,K]).  workspace: *_workspace(B,N,K) bytes. */
+size_t ddsp_b200_oscillator_bank_workspace(int B, int N, int K);
+int ddsp_b200_oscillator_bank(const float* frequency_envelopes,
+                              const float* amplitude_envelopes, float* out, int B,
+                              int N, int K, float sample_rate, int sum_sinusoids,
+                              void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* core.resample / core.upsample_with_windows (core.py:573-714) stand-alone:
  * in [B,F,C] -> out [B,N,C].  method: 0 'window', 1 'linear', 2 'nearest'
  * ('cubic' is not built).  add_endpoint as in the reference. */

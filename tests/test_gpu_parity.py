@@ -296,3 +296,47 @@ def test_resample_multi_dimensional_inputs(dimensions):
   rnd = np.random.default_rng(0).standard_normal((3, 20, 7)).astype(np.float32)
   got = _np(core.upsample_with_windows(rnd, 640))
   np.testing.assert_allclose(got, oracle.upsample_with_windows(rnd, 640), atol=2e-6)
+
+
+def test_normalize_harmonics_and_helpers():
+  """core_test.py:104-142 (get_harmonic_frequencies / normalize_harmonics)."""
+  f0 = np.array([[[1000.0], [3000.0], [4500.0], [9000.0]]], np.float32)
+  hd = np.ones((1, 4, 3), np.float32)
+  out = _np(core.normalize_harmonics(hd, f0, 16000))
+  np.testing.assert_allclose(out[0, 0], [1 / 3] * 3, rtol=1e-6)
+  np.testing.assert_allclose(out[0, 1], [0.5, 0.5, 0.0], rtol=1e-6)
+  np.testing.assert_allclose(out[0, 2], [1.0, 0.0, 0.0], rtol=1e-6)
+  np.testing.assert_allclose(out[0, 3], [0.0, 0.0, 0.0])
+  plain = _np(core.normalize_harmonics(hd * 2.0))
+  np.testing.assert_allclose(plain, np.full((1, 4, 3), 1 / 3), rtol=1e-6)
+  hf = _np(core.get_harmonic_frequencies(f0, 3))
+  np.testing.assert_allclose(hf[0, :, 2], f0[0, :, 0] * 3)
+  amps = _np(core.remove_above_nyquist(hf, np.ones_like(hf), 16000))
+  assert np.array_equal(amps == 0, hf >= 8000.0)
+
+
+@pytest.mark.parametrize('sum_sinusoids', [True, False])
+@pytest.mark.parametrize('B,N,K', [(2, 1600, 3), (1, 4000, 100), (3, 257, 37)])
+def test_oscillator_bank_matches_oracle(B, N, K, sum_sinusoids):
+  """core.oscillator_bank (core.py:911-962) on audio-rate envelopes; shapes as in
+  core_test.py:460-482, Nyquist silence as in core_test.py:484-503."""
+  rng = np.random.default_rng(N + K)
+  f = (rng.uniform(50, 9000, (B, 1, K)) *
+       (1.0 + 0.01 * np.sin(np.arange(N) / 300.0))[None, :, None]).astype(np.float32)
+  a = rng.uniform(0.0, 1.0, (B, N, K)).astype(np.float32)
+  want = oracle.oscillator_bank(f, a, sum_sinusoids=sum_sinusoids, dtype=np.float64)
+  got = _np(core.oscillator_bank(f, a, sum_sinusoids=sum_sinusoids))
+  assert got.shape == want.shape
+  emax, el2 = rel_err(got, want)
+  assert emax < TOL and el2 < TOL, (emax, el2)
+
+
+@pytest.mark.parametrize('sample_rate', [4000, 16000, 44100])
+def test_oscillator_bank_silent_above_nyquist(sample_rate):
+  """core_test.py:484-503 verbatim."""
+  nyquist = sample_rate / 2
+  freqs = np.array([1.1, 1.5, 2.0]) * nyquist
+  ones = np.ones([2, 16000, 3], np.float32)
+  wav = _np(core.oscillator_bank(ones * freqs.astype(np.float32), ones,
+                                 sample_rate=sample_rate))
+  assert wav.shape == (2, 16000) and np.all(wav == 0.0)
