@@ -234,6 +234,8 @@ noise_backward_kernel(NoiseBwdParams p) {
     ir_tap(p.g, j, &idx, &w);
     sWin[j] = w;
   }
+  for (int e = tid; e < 32 * p.xS; e += kNbThreads) sX[e] = 0.f;   // pads stay zero
+  for (int e = tid; e < 32 * p.gS; e += kNbThreads) sG[e] = 0.f;
   __syncthreads();
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int b = tile / p.tiles_per_item;
@@ -266,18 +268,25 @@ noise_backward_kernel(NoiseBwdParams p) {
       const float* xrow = sX + lane * p.xS;
       const float* grow = sG + lane * p.gS;
       float* hrow = sH + lane * p.hS;
-      for (int m0 = warp * 8; m0 < S; m0 += (kNbThreads / 32) * 8) {
-        float acc[8];
+      // 16 taps per round; the 16-value window gy[i + m0 .. i + m0 + 15] slides
+      // by one per input sample: 2 LDS feed 16 FFMA (rows are zero padded).
+      const int nchunk = (frame + 15) >> 4;
+      for (int m0 = warp * 16; m0 < S; m0 += (kNbThreads / 32) * 16) {
+        float acc[16], W[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-        for (int i = 0; i < frame; ++i) {
-          const float xv = xrow[i];
+        for (int c = 0; c < 16; ++c) { acc[c] = 0.f; W[c] = grow[m0 + c]; }
+        for (int ch = 0; ch < nchunk; ++ch) {
+          const int ib = ch << 4;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (m0 + c < S) acc[c] = fmaf(xv, grow[i + m0 + c], acc[c]);
+          for (int u = 0; u < 16; ++u) {
+            const float xv = xrow[ib + u];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = fmaf(xv, W[(c + u) & 15], acc[c]);
+            W[u & 15] = grow[ib + u + 1 + m0 + 15];
+          }
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < 16; ++c)
           if (m0 + c < S) hrow[m0 + c] = acc[c] * sWin[m0 + c];
       }
     }

@@ -483,8 +483,8 @@ int ddsp_b200_filtered_noise_backward(const float* grad_audio, const float* nois
                "filtered_noise_backward: impulse response too short");
   p.ylen = frame + p.S - 1;
   p.nh = p.g.S0 / 2 + 1;
-  p.xS = frame | 1;
-  p.gS = p.ylen | 1;
+  p.xS = (((frame + 15) & ~15) + 1) | 1;
+  p.gS = (((frame + 15) & ~15) + p.S + 17) | 1;
   p.hS = (p.S + p.nh) | 1;
   p.tiles_per_item = (F + 31) / 32;
   const long long n_tiles = (long long)B * p.tiles_per_item;

@@ -125,9 +125,9 @@ harmonic_generic_kernel(HarmonicParams p) {
       int r = idx / K, c = idx - r * K;
       sX[r * Kp + c] = hdb[idx];
     }
-    if (rows_in < nfr + 1) {                    // replicate the last frame
-      for (int c = tid; c < K; c += kHarmThreads)
-        sX[nfr * Kp + c] = sX[(nfr - 1) * Kp + c];
+    if (rows_in < nfr + 1) {                    // frame F := frame F-1 (from HBM:
+      for (int c = tid; c < K; c += kHarmThreads)  // the smem row is not synced yet)
+        sX[nfr * Kp + c] = hdb[(size_t)(nfr - 1) * K + c];
     }
   } else {
     for (int j = tid; j <= nfr; j += kHarmThreads) sX[j * Kp] = 1.0f;

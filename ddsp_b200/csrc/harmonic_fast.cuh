@@ -447,9 +447,11 @@ inline bool harmonic_fast_supported(const HarmonicParams& p) {
 inline int launch_harmonic_fast(HarmonicParams p, cudaStream_t st) {
   p.Kp = (p.K + 3) & ~3;
   // debug / tuning knobs (not part of the ABI): threads per CTA and frames per tile
-  static const int env_nt = [] { const char* e = getenv("DDSP_B200_HARM_NT"); return e ? atoi(e) : 256; }();
+  static const int env_nt = [] { const char* e = getenv("DDSP_B200_HARM_NT"); return e ? atoi(e) : 128; }();
   static const int env_ft = [] { const char* e = getenv("DDSP_B200_HARM_FT"); return e ? atoi(e) : 0; }();
-  const int NT = (env_nt == 128) ? 128 : 256;
+  // 4-warp CTAs (16 frames) measured 4 % faster than 8-warp ones (32 frames):
+  // more resident CTAs, cheaper CTA-wide barriers (profiles/README.md).
+  const int NT = (env_nt == 256) ? 256 : 128;
   int FT = std::max(1, 2048 / p.hop);
   if (NT == 128) FT = std::max(1, FT / 2);
   if (env_ft > 0) FT = std::min(FT, env_ft);
@@ -461,7 +463,7 @@ inline int launch_harmonic_fast(HarmonicParams p, cudaStream_t st) {
     // Wave quantisation: with ~3 resident CTAs per SM a grid of a few waves can
     // leave a third of the chip idle in the last one.  Halve the tile (at most
     // twice) when that buys more than 8 % of wave efficiency.
-    const double slots = 3.0 * kNumSMs;
+    const double slots = (NT == 128 ? 6.0 : 3.0) * kNumSMs;
     auto eff = [&](int ft) {
       const double n = (double)p.B * ((p.F + ft - 1) / ft);
       return n / (std::ceil(n / slots) * slots);

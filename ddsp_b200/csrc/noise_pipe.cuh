@@ -155,23 +155,31 @@ noise_pipe_kernel(NoisePipeParams p) {
       // A. magnitudes -> lane-private rows (exp_sigmoid fused)
       mbar_wait(&sm.rawbar, it & 1);
       named_bar(1, PT);            // every producer is done reading sm.m (previous tile)
+      // columns 0..63: two full-warp passes per row; column 64: one lane per row
       for (int jl = pw; jl < 32; jl += PROD_WARPS) {
         const int j = j0 + jl;
         const float* src = sm.raw + roff + jl * NB;
         float* dst = sm.m + jl * MS;
-        const bool live = (j >= 0 && j < p.F);
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-          const int k = lane + 32 * kk;
-          if (k < NB) {
-            float v = 0.f;
-            if (live) {
-              v = src[k];
-              if (p.raw) v = exp_sigmoid_f(v + p.bias);       // synths.py:176-177
-            }
-            dst[k] = v;
+        float v0 = 0.f, v1 = 0.f;
+        if (j >= 0 && j < p.F) {
+          v0 = src[lane];
+          v1 = src[lane + 32];
+          if (p.raw) {                                      // synths.py:176-177
+            v0 = exp_sigmoid_f(v0 + p.bias);
+            v1 = exp_sigmoid_f(v1 + p.bias);
           }
         }
+        dst[lane] = v0;
+        dst[lane + 32] = v1;
+      }
+      if (pw == PROD_WARPS - 1) {
+        const int j = j0 + lane;
+        float v = 0.f;
+        if (j >= 0 && j < p.F) {
+          v = sm.raw[roff + lane * NB + 64];
+          if (p.raw) v = exp_sigmoid_f(v + p.bias);
+        }
+        sm.m[lane * MS + 64] = v;
       }
       named_bar(1, PT);            // sm.raw consumed, sm.m complete
       {
