@@ -52,59 +52,81 @@ def _measured_peaks():
 
 
 class ClockSampler:
-  """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-  QUERY = ('clocks.sm,clocks.max.sm,power.draw,'
-           'clocks_event_reasons.hw_slowdown,'
-           'clocks_event_reasons.hw_thermal_slowdown,'
-           'clocks_event_reasons.sw_thermal_slowdown,'
-           'clocks_event_reasons.sw_power_cap')
+  """Samples SM clocks / throttle reasons through NVML while the GPU is under
+  load.  A step of this workload is tens of microseconds, so a polling
+  `nvidia-smi -lms` process never lands a sample inside a short timed region;
+  an in-process NVML thread polls every ~1 ms instead.  Samples are stamped so
+  the timed window can be separated from the rest of the load window."""
+  REASONS = {
+      'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40,
+      'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4,
+  }
 
   def __init__(self, index):
     self.index = index
-    self.rows = []
-    self.proc = None
+    self.samples = []            # (t, sm_mhz, reasons bitmask)
+    self.smax = None
+    self.stop_flag = False
+    self.thread = None
+    self.err = None
+    self.t_timed = [None, None]
 
   def start(self):
     try:
-      self.proc = subprocess.Popen(
-          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-           '--format=csv,noheader,nounits', '-lms', '50'],
-          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-      self.thread = threading.Thread(target=self._read, daemon=True)
-      self.thread.start()
-    except OSError:
-      self.proc = None
+      import pynvml
+      import torch
+      pynvml.nvmlInit()
+      try:
+        uuid = 'GPU-' + str(torch.cuda.get_device_properties(self.index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+      except Exception:  # pylint: disable=broad-except
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+      self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+      get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons',
+                            None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
 
-  def _read(self):
-    for line in self.proc.stdout:
-      self.rows.append(line.strip())
+      def loop():
+        while not self.stop_flag:
+          try:
+            mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            rs = int(get_reasons(h))
+            self.samples.append((time.perf_counter(), mhz, rs))
+          except Exception as e:  # pylint: disable=broad-except
+            self.err = repr(e)
+            return
+          time.sleep(0.0005)
+
+      self.thread = threading.Thread(target=loop, daemon=True)
+      self.thread.start()
+    except Exception as e:  # pylint: disable=broad-except
+      self.err = repr(e)
+
+  def mark_timed(self, which):
+    self.t_timed[which] = time.perf_counter()
 
   def stop(self):
-    if self.proc is None:
-      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi absent']}
-    time.sleep(0.06)
-    self.proc.terminate()
-    try:
-      self.proc.wait(timeout=2)
-    except subprocess.TimeoutExpired:
-      self.proc.kill()
-    sm, smax, reasons = [], None, set()
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-             'sw_power_cap']
-    for row in self.rows:
-      parts = [p.strip() for p in row.split(',')]
-      if len(parts) < 7:
-        continue
-      try:
-        sm.append(float(parts[0]))
-        smax = float(parts[1])
-      except ValueError:
-        continue
-      for name, val in zip(names, parts[3:7]):
-        if val.lower().startswith('active'):
-          reasons.add(name)
-    return {'sm_mhz': statistics.median(sm) if sm else None,
-            'sm_max_mhz': smax, 'samples': len(sm), 'reasons': sorted(reasons)}
+    self.stop_flag = True
+    if self.thread is not None:
+      self.thread.join(timeout=2)
+    if not self.samples:
+      return {'sm_mhz': None, 'sm_max_mhz': self.smax, 'samples': 0,
+              'reasons': ['nvml unavailable: %s' % self.err]}
+    t0, t1 = self.t_timed
+    window = 'timed region'
+    rows = [r for r in self.samples if t0 is not None and t1 is not None and
+            t0 <= r[0] <= t1]
+    if len(rows) < 3:
+      # a short timed region (K steps of ~70 us): use every sample taken while
+      # this process kept the GPU busy (warm-up, timed, e2e and per-kernel loops)
+      rows = self.samples
+      window = 'load window (warm-up + timed + e2e + per-kernel loops)'
+    mask = 0
+    for r in rows:
+      mask |= r[2]
+    reasons = sorted(k for k, bit in self.REASONS.items() if mask & bit)
+    return {'sm_mhz': statistics.median(r[1] for r in rows),
+            'sm_max_mhz': self.smax, 'samples': len(rows), 'window': window,
+            'reasons': reasons}
 
 
 def make_host_inputs(batch, seed):
@@ -224,7 +246,7 @@ def run_ours(args):
       dist.barrier()
       torch.cuda.synchronize()
 
-  def timed(fn, steps, warmup, collective=True):
+  def timed(fn, steps, warmup, collective=True, mark=None):
     """CUDA-event time of `steps` calls; `collective=False` for rank-local
     measurements (no barrier / all-reduce: the other ranks are not here)."""
     for i in range(warmup):
@@ -232,11 +254,15 @@ def run_ours(args):
     barrier(collective)
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
+    if mark is not None:
+      mark.mark_timed(0)
     e0.record()
     for i in range(steps):
       fn(warmup + i)
     e1.record()
     barrier(collective)
+    if mark is not None:
+      mark.mark_timed(1)
     ms = e0.elapsed_time(e1)
     if world > 1 and collective:
       tms = torch.tensor([ms], device=dev)
@@ -252,10 +278,10 @@ def run_ours(args):
   if rank == 0:
     sampler.start()
   c0 = lib.ddsp_b200_launch_count()
-  ms_total = timed(step_resident, args.steps, args.warmup)
+  ms_total = timed(step_resident, args.steps, args.warmup,
+                   mark=sampler if rank == 0 else None)
   launches = lib.ddsp_b200_launch_count() - c0
   launches_timed = launches * args.steps // (args.steps + args.warmup)
-  clocks = sampler.stop() if rank == 0 else None
   ms_per_step = ms_total / args.steps
   value = world * B * N_SAMPLES / (ms_per_step * 1e-3)
 
@@ -294,6 +320,7 @@ def run_ours(args):
   ms_harm = timed(harm_only, k_steps, 5) / k_steps
   ms_noise = timed(noise_only, k_steps, 5) / k_steps
   ms_ctl = timed(controls_only, k_steps, 5) / k_steps
+  clocks = sampler.stop() if rank == 0 else None
 
   # -- secondary workload: C3 (B=256) for context ------------------------------
   extra = {}
