@@ -286,14 +286,29 @@ def run_ours(args):
   value = world * B * N_SAMPLES / (ms_per_step * 1e-3)
 
   # -- e2e: host buffers in, host audio out, copies inside the timed region ---
+  # The public host-buffer call: HostDecoder = ProcessorGroup over pinned host
+  # arrays through ddsp_b200_decoder_forward_host (chunked copy / compute / copy
+  # pipeline on three streams).  Every step copies all inputs H2D and the whole
+  # audio D2H and waits for it.
+  host_dec = ddsp_b200.HostDecoder(group, max_batch=B, n_frames=N_FRAMES,
+                                   n_harmonics=N_HARM, n_bands=N_BANDS,
+                                   n_chunks=args.chunks)
+
   def step_e2e(i):
+    host_dec(pinned, out=out_host, sync=True)   # the caller reads the result
+
+  e2e_steps = max(args.steps, 20)
+  ms_e2e = timed(step_e2e, e2e_steps, max(3, args.warmup // 2)) / e2e_steps
+  e2e_value = world * B * N_SAMPLES / (ms_e2e * 1e-3)
+
+  # the same round trip without the pipeline (4 copies, one call, one copy)
+  def step_e2e_serial(i):
     feats = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
     audio = group(feats)
     out_host.copy_(audio, non_blocking=True)
-    torch.cuda.current_stream().synchronize()   # the caller reads the result
+    torch.cuda.current_stream().synchronize()
 
-  ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2)) / args.steps
-  e2e_value = world * B * N_SAMPLES / (ms_e2e * 1e-3)
+  ms_e2e_serial = timed(step_e2e_serial, e2e_steps, 3) / e2e_steps
 
   # -- per-kernel durations for the roofline (rank 0 reports) -----------------
   ctl = []
@@ -412,7 +427,10 @@ def run_ours(args):
           'noise': 'in-kernel Philox4x32-10', 'parallelism': 'batch-sharded replicas, no collective',
       },
       'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e,
-              'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},
+              'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
+              'api': 'ddsp_b200.HostDecoder(group)(pinned host inputs) -> pinned '
+                     'host audio, %d chunks on 3 streams' % args.chunks,
+              'ms_per_step_unpipelined': ms_e2e_serial},
       'gpu_launches': int(launches_timed),
       'clocks': clocks,
       'roofline': roofline,
@@ -451,6 +469,8 @@ def _main():
   ap.add_argument('--batch', type=int, default=BATCH_PER_GPU,
                   help='batch items per GPU (configs[1] = 32)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--chunks', type=int, default=8,
+                  help='chunks of the host-buffer (e2e) pipeline')
   ap.add_argument('--extra', type=int, default=1,
                   help='also time the B=256 (configs[2]) step on rank 0')
   args = ap.parse_args()

@@ -58,6 +58,12 @@ SIGNATURES = {
     'ddsp_b200_decoder_forward':
         (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _f,
               _i, _i, _i, _f, _vp]),
+    'ddsp_b200_host_pipeline_create':
+        (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
+    'ddsp_b200_host_pipeline_destroy': (_i, [_vp]),
+    'ddsp_b200_decoder_forward_host':
+        (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _i, _i, _f, _i, _i, _i,
+              _f, _vp]),
     'ddsp_b200_harmonic_backward':
         (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'ddsp_b200_filtered_noise_backward':

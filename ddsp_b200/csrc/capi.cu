@@ -13,6 +13,7 @@
 #include "noise.cuh"
 #include "noise_fused.cuh"
 #include "noise_pipe.cuh"
+#include "host_pipeline.cuh"
 #include "backward.cuh"
 #include "oscbank.cuh"
 
@@ -362,13 +363,13 @@ int ddsp_b200_filtered_noise_forward(const float* mags, const float* noise,
                                     DDSP_B200_PAD_SAME, -1, accumulate, stream);
 }
 
-int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
-                              const float* f0_hz, const float* mags_raw,
-                              const float* noise, uint64_t seed, uint64_t offset,
-                              float* audio, int B, int F, int K, int nb, int N,
-                              float sample_rate, int amp_method,
-                              int harmonic_flags, int window_size,
-                              float initial_bias, void* stream) {
+static int decoder_forward_impl(const float* amps_raw, const float* hd_raw,
+                                const float* f0_hz, const float* mags_raw,
+                                const float* noise, uint64_t seed, uint64_t offset,
+                                float* audio, int B, int F, int K, int nb, int N,
+                                float sample_rate, int amp_method,
+                                int harmonic_flags, int window_size,
+                                float initial_bias, void* stream, int item_base) {
   DDSP_REQUIRE(amps_raw && hd_raw && f0_hz && mags_raw && audio,
                DDSP_B200_E_INVALID, "decoder_forward: null pointer");
   DDSP_REQUIRE(B >= 0 && F >= 1 && K >= 1 && N >= 1 && nb >= 2,
@@ -412,7 +413,150 @@ int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
   if (rc) return rc;
   return launch_noise_best(mags_raw, noise, seed, offset, audio, B, F, nb, N,
                            window_size, /*accumulate=*/1, st, /*raw=*/1,
-                           initial_bias);
+                           initial_bias, item_base);
+}
+
+int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
+                              const float* f0_hz, const float* mags_raw,
+                              const float* noise, uint64_t seed, uint64_t offset,
+                              float* audio, int B, int F, int K, int nb, int N,
+                              float sample_rate, int amp_method,
+                              int harmonic_flags, int window_size,
+                              float initial_bias, void* stream) {
+  return decoder_forward_impl(amps_raw, hd_raw, f0_hz, mags_raw, noise, seed, offset,
+                              audio, B, F, K, nb, N, sample_rate, amp_method,
+                              harmonic_flags, window_size, initial_bias, stream, 0);
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------
+#define DDSP_CUDA_TRY(expr, what)                                         \
+  do {                                                                    \
+    cudaError_t e__ = (expr);                                             \
+    if (e__ != cudaSuccess) {                                             \
+      ::ddsp::set_error("%s: %s", what, cudaGetErrorString(e__));         \
+      return DDSP_B200_E_CUDA;                                            \
+    }                                                                     \
+  } while (0)
+
+int ddsp_b200_host_pipeline_create(ddsp_b200_host_pipeline** out, int max_B, int F,
+                                   int K, int nb, int N, int max_chunks) {
+  DDSP_REQUIRE(out != nullptr, DDSP_B200_E_INVALID, "host_pipeline_create: null out");
+  *out = nullptr;
+  DDSP_REQUIRE(max_B >= 1 && F >= 1 && K >= 1 && nb >= 2 && N >= 1 && max_chunks >= 1,
+               DDSP_B200_E_INVALID,
+               "host_pipeline_create: bad shape max_B=%d F=%d K=%d nb=%d N=%d chunks=%d",
+               max_B, F, K, nb, N, max_chunks);
+  HostPipeline* hp = new HostPipeline();
+  auto fail = [&](const char* what, cudaError_t e) {
+    set_error("host_pipeline_create: %s: %s", what, cudaGetErrorString(e));
+    host_pipeline_free(hp);
+    return DDSP_B200_E_CUDA;
+  };
+  cudaError_t e = cudaGetDevice(&hp->device);
+  if (e != cudaSuccess) { hp->device = -1; return fail("cudaGetDevice", e); }
+  hp->max_B = max_B; hp->F = F; hp->K = K; hp->nb = nb; hp->N = N;
+  hp->max_chunks = std::min(max_chunks, max_B);
+  // every sub-buffer starts on a 256-byte boundary (TMA bulk copies want 16)
+  auto pad = [](size_t n) { return (n + 63) & ~(size_t)63; };
+  const size_t n_amps = pad((size_t)max_B * F), n_hd = pad((size_t)max_B * F * K),
+               n_mags = pad((size_t)max_B * F * nb), n_audio = pad((size_t)max_B * N);
+  const size_t total = 2 * n_amps + n_hd + n_mags + n_audio;
+  if ((e = cudaMalloc(&hp->d_base, total * sizeof(float))) != cudaSuccess)
+    return fail("cudaMalloc(staging)", e);
+  hp->d_amps = hp->d_base;
+  hp->d_f0 = hp->d_amps + n_amps;
+  hp->d_hd = hp->d_f0 + n_amps;
+  hp->d_mags = hp->d_hd + n_hd;
+  hp->d_audio = hp->d_mags + n_mags;
+  if ((e = cudaStreamCreateWithFlags(&hp->s_h2d, cudaStreamNonBlocking)) != cudaSuccess)
+    return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&hp->s_d2h, cudaStreamNonBlocking)) != cudaSuccess)
+    return fail("cudaStreamCreate", e);
+  if ((e = cudaEventCreateWithFlags(&hp->ev_start, cudaEventDisableTiming)) != cudaSuccess)
+    return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&hp->ev_done, cudaEventDisableTiming)) != cudaSuccess)
+    return fail("cudaEventCreate", e);
+  for (int c = 0; c < hp->max_chunks; ++c) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    if ((e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming)) != cudaSuccess)
+      return fail("cudaEventCreate", e);
+    hp->ev_h2d.push_back(a);
+    if ((e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming)) != cudaSuccess)
+      return fail("cudaEventCreate", e);
+    hp->ev_comp.push_back(b);
+  }
+  *out = reinterpret_cast<ddsp_b200_host_pipeline*>(hp);
+  return 0;
+}
+
+int ddsp_b200_host_pipeline_destroy(ddsp_b200_host_pipeline* handle) {
+  host_pipeline_free(reinterpret_cast<HostPipeline*>(handle));
+  return 0;
+}
+
+int ddsp_b200_decoder_forward_host(ddsp_b200_host_pipeline* handle,
+                                   const float* amps_raw, const float* hd_raw,
+                                   const float* f0_hz, const float* mags_raw,
+                                   uint64_t seed, uint64_t offset, float* audio,
+                                   int B, int n_chunks, float sample_rate,
+                                   int amp_method, int harmonic_flags,
+                                   int window_size, float initial_bias,
+                                   void* stream) {
+  HostPipeline* hp = reinterpret_cast<HostPipeline*>(handle);
+  DDSP_REQUIRE(hp != nullptr, DDSP_B200_E_INVALID, "decoder_forward_host: null handle");
+  DDSP_REQUIRE(amps_raw && hd_raw && f0_hz && mags_raw && audio, DDSP_B200_E_INVALID,
+               "decoder_forward_host: null pointer");
+  DDSP_REQUIRE(B >= 0 && B <= hp->max_B, DDSP_B200_E_INVALID,
+               "decoder_forward_host: B=%d outside [0, %d]", B, hp->max_B);
+  if (B == 0) return 0;
+  int dev = 0;
+  DDSP_CUDA_TRY(cudaGetDevice(&dev), "decoder_forward_host: cudaGetDevice");
+  DDSP_REQUIRE(dev == hp->device, DDSP_B200_E_INVALID,
+               "decoder_forward_host: pipeline belongs to device %d, current is %d",
+               hp->device, dev);
+  n_chunks = std::max(1, std::min(std::min(n_chunks, hp->max_chunks), B));
+  const int F = hp->F, K = hp->K, nb = hp->nb, N = hp->N;
+  cudaStream_t st = (cudaStream_t)stream;
+  // Order this call after whatever the caller queued on `st`, and after the
+  // previous call's last device->host copy (the staging buffers are reused).
+  DDSP_CUDA_TRY(cudaEventRecord(hp->ev_start, st), "decoder_forward_host: event");
+  DDSP_CUDA_TRY(cudaStreamWaitEvent(hp->s_h2d, hp->ev_start, 0), "decoder_forward_host: wait");
+  if (hp->used)
+    DDSP_CUDA_TRY(cudaStreamWaitEvent(hp->s_h2d, hp->ev_done, 0), "decoder_forward_host: wait");
+  hp->used = true;
+  const int per = (B + n_chunks - 1) / n_chunks;
+  int c = 0;
+  for (int b0 = 0; b0 < B; b0 += per, ++c) {
+    const int nbi = std::min(per, B - b0);
+    const size_t o1 = (size_t)b0 * F;
+    DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_f0 + o1, f0_hz + o1, sizeof(float) * nbi * F,
+                                  cudaMemcpyHostToDevice, hp->s_h2d), "decoder_forward_host: H2D f0");
+    DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_amps + o1, amps_raw + o1, sizeof(float) * nbi * F,
+                                  cudaMemcpyHostToDevice, hp->s_h2d), "decoder_forward_host: H2D amps");
+    DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_hd + o1 * K, hd_raw + o1 * K,
+                                  sizeof(float) * (size_t)nbi * F * K,
+                                  cudaMemcpyHostToDevice, hp->s_h2d), "decoder_forward_host: H2D hd");
+    DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_mags + o1 * nb, mags_raw + o1 * nb,
+                                  sizeof(float) * (size_t)nbi * F * nb,
+                                  cudaMemcpyHostToDevice, hp->s_h2d), "decoder_forward_host: H2D mags");
+    DDSP_CUDA_TRY(cudaEventRecord(hp->ev_h2d[c], hp->s_h2d), "decoder_forward_host: event");
+    DDSP_CUDA_TRY(cudaStreamWaitEvent(st, hp->ev_h2d[c], 0), "decoder_forward_host: wait");
+    int rc = decoder_forward_impl(hp->d_amps + o1, hp->d_hd + o1 * K, hp->d_f0 + o1,
+                                  hp->d_mags + o1 * nb, nullptr, seed, offset,
+                                  hp->d_audio + (size_t)b0 * N, nbi, F, K, nb, N,
+                                  sample_rate, amp_method, harmonic_flags, window_size,
+                                  initial_bias, stream, b0);
+    if (rc) return rc;
+    DDSP_CUDA_TRY(cudaEventRecord(hp->ev_comp[c], st), "decoder_forward_host: event");
+    DDSP_CUDA_TRY(cudaStreamWaitEvent(hp->s_d2h, hp->ev_comp[c], 0), "decoder_forward_host: wait");
+    DDSP_CUDA_TRY(cudaMemcpyAsync(audio + (size_t)b0 * N, hp->d_audio + (size_t)b0 * N,
+                                  sizeof(float) * (size_t)nbi * N, cudaMemcpyDeviceToHost,
+                                  hp->s_d2h), "decoder_forward_host: D2H audio");
+  }
+  DDSP_CUDA_TRY(cudaEventRecord(hp->ev_done, hp->s_d2h), "decoder_forward_host: event");
+  // The caller's stream completes when the audio is in host memory.
+  DDSP_CUDA_TRY(cudaStreamWaitEvent(st, hp->ev_done, 0), "decoder_forward_host: wait");
+  return 0;
 }
 
 int ddsp_b200_harmonic_backward(const float* f0_hz, const float* grad_audio,

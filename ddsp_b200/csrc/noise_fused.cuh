@@ -47,6 +47,7 @@ struct NoiseFusedParams {
   float* audio;                     // [B,N]
   uint64_t seed, offset;
   int B, F, nb, N, frame, start, accumulate;
+  int item_base;                    // Philox item index of batch row 0
   int raw;                          // mags are raw network outputs:
   float bias;                       //   exp_sigmoid(x + bias) while staging
   int TFo, Hb, Ha;                  // output frames per tile, halo before/after
@@ -273,7 +274,7 @@ noise_fused_kernel(NoiseFusedParams p) {
           int jl, qd;
           if (p.nq_shift >= 0) { jl = e >> p.nq_shift; qd = e & (nq - 1); }
           else { jl = e / nq; qd = e - jl * nq; }
-          const float4 r = noise4(qbase + (uint32_t)e, (uint32_t)b, p.seed, p.offset);
+          const float4 r = noise4(qbase + (uint32_t)e, (uint32_t)(b + p.item_base), p.seed, p.offset);
           float2* d = reinterpret_cast<float2*>(sX + jl * p.xS + 4 * qd);
           d[0] = make_float2(r.x, r.y);
           d[1] = make_float2(r.z, r.w);
@@ -290,7 +291,7 @@ noise_fused_kernel(NoiseFusedParams p) {
               if (pp + 2 < p.N) v2 = nzb[pp + 2];
               if (pp + 3 < p.N) v3 = nzb[pp + 3];
             } else {
-              const float4 r = noise4((uint32_t)(pp >> 2), (uint32_t)b, p.seed,
+              const float4 r = noise4((uint32_t)(pp >> 2), (uint32_t)(b + p.item_base), p.seed,
                                       p.offset);
               v0 = r.x;
               if (pp + 1 < p.N) v1 = r.y;
@@ -476,8 +477,9 @@ inline int launch_noise_fused(const float* mags, const float* noise,
                               uint64_t seed, uint64_t offset, float* audio,
                               int B, int F, int nb, int N, int window_size,
                               int accumulate, cudaStream_t st, int raw = 0,
-                              float bias = 0.f) {
+                              float bias = 0.f, int item_base = 0) {
   NoiseFusedParams p;
+  p.item_base = item_base;
   if (!nf_configure(p, F, nb, N, window_size)) {
     set_error("filtered_noise_forward: shape outside the fused path");
     return DDSP_B200_E_UNSUPPORTED;

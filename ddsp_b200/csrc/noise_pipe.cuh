@@ -74,6 +74,7 @@ struct NoisePipeParams {
   int B, F, N, accumulate, raw;
   float bias;
   int tiles_per_item, n_tiles;
+  int item_base;   // Philox item index of batch row 0 (chunked host pipeline)
 };
 
 __global__ void __launch_bounds__(np_::THREADS, 1)
@@ -252,7 +253,7 @@ noise_pipe_kernel(NoisePipeParams p) {
           const uint32_t qbase = (uint32_t)(p_lo >> 2);
           for (int e = e_lo + lane; e < e_hi; e += 32) {
             const int jl = e >> 4, qd = e & 15;
-            const float4 r = noise4(qbase + (uint32_t)e, (uint32_t)b, p.seed, p.offset);
+            const float4 r = noise4(qbase + (uint32_t)e, (uint32_t)(b + p.item_base), p.seed, p.offset);
             float2* d = reinterpret_cast<float2*>(xs + jl * XS + 4 * qd);
             d[0] = make_float2(r.x, r.y);
             d[1] = make_float2(r.z, r.w);
@@ -267,7 +268,7 @@ noise_pipe_kernel(NoisePipeParams p) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) if (pp + u < p.N) v[u] = nzb[pp + u];
               } else {
-                const float4 r = noise4((uint32_t)(pp >> 2), (uint32_t)b, p.seed,
+                const float4 r = noise4((uint32_t)(pp >> 2), (uint32_t)(b + p.item_base), p.seed,
                                         p.offset);
                 v[0] = r.x;
                 if (pp + 1 < p.N) v[1] = r.y;
@@ -420,8 +421,10 @@ inline bool noise_pipe_supported(int F, int nb, int N, int window_size) {
 
 inline int launch_noise_pipe(const float* mags, const float* noise, uint64_t seed,
                              uint64_t offset, float* audio, int B, int F, int N,
-                             int accumulate, cudaStream_t st, int raw, float bias) {
+                             int accumulate, cudaStream_t st, int raw, float bias,
+                             int item_base = 0) {
   NoisePipeParams p;
+  p.item_base = item_base;
   p.mags = mags; p.noise = noise; p.audio = audio; p.seed = seed; p.offset = offset;
   p.B = B; p.F = F; p.N = N; p.accumulate = accumulate; p.raw = raw; p.bias = bias;
   p.tiles_per_item = (F + np_::TFO - 1) / np_::TFO;
@@ -450,12 +453,13 @@ inline int launch_noise_pipe(const float* mags, const float* noise, uint64_t see
 inline int launch_noise_best(const float* mags, const float* noise, uint64_t seed,
                              uint64_t offset, float* audio, int B, int F, int nb,
                              int N, int window_size, int accumulate,
-                             cudaStream_t st, int raw = 0, float bias = 0.f) {
+                             cudaStream_t st, int raw = 0, float bias = 0.f,
+                            int item_base = 0) {
   if (noise_pipe_supported(F, nb, N, window_size))
     return launch_noise_pipe(mags, noise, seed, offset, audio, B, F, N, accumulate,
-                             st, raw, bias);
+                             st, raw, bias, item_base);
   return launch_noise_fused(mags, noise, seed, offset, audio, B, F, nb, N,
-                            window_size, accumulate, st, raw, bias);
+                            window_size, accumulate, st, raw, bias, item_base);
 }
 
 }  // namespace ddsp

@@ -12,7 +12,8 @@
  *   - All tensors are contiguous row-major float32 in DEVICE memory of the
  *     current CUDA device.  Controls are [B, F, C]; audio is [B, N].
  *   - The caller allocates every input, output and workspace.  The library never
- *     allocates, frees or retains a pointer past the call.
+ *     allocates, frees or retains a pointer past the call (one exception, with
+ *     explicit create/destroy: ddsp_b200_host_pipeline, below).
  *   - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous and
  *     re-entrant; there is no global mutable state (the last-error string is
  *     thread-local).
@@ -162,6 +163,36 @@ int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
                               float sample_rate, int amp_method,
                               int harmonic_flags, int window_size,
                               float initial_bias, void* stream);
+
+/* The same decoder for HOST buffers - what a caller of the reference's
+ * ProcessorGroup.__call__ holds when its network outputs are numpy arrays
+ * (processors_test.py:35-42) and it wants numpy audio back.  The batch is cut
+ * into n_chunks groups of items; chunk c's host->device copies, its two kernels
+ * and its device->host audio copy run on three streams and overlap with the
+ * neighbouring chunks', so the call costs about max(H2D, compute, D2H) instead
+ * of their sum.  Results are identical to ddsp_b200_decoder_forward on the whole
+ * batch (the Philox item index of a chunk's rows is offset accordingly).
+ *
+ * The pipeline handle owns one device staging allocation for max_B items of
+ * shape (F, K, nb, N), two copy streams and the events - the only objects this
+ * library ever allocates; *_destroy releases them.  A handle belongs to the
+ * device that was current at creation and serialises its own calls.
+ * amps_raw/f0_hz [B,F,1], hd_raw [B,F,K], mags_raw [B,F,nb], audio [B,N]: HOST
+ * pointers, pinned (cudaHostAlloc / cudaHostRegister) for the copies to be
+ * asynchronous.  The call returns once everything is queued; `stream` completes
+ * when the audio is in host memory. */
+typedef struct ddsp_b200_host_pipeline ddsp_b200_host_pipeline;
+int ddsp_b200_host_pipeline_create(ddsp_b200_host_pipeline** out, int max_B, int F,
+                                   int K, int nb, int N, int max_chunks);
+int ddsp_b200_host_pipeline_destroy(ddsp_b200_host_pipeline* pipeline);
+int ddsp_b200_decoder_forward_host(ddsp_b200_host_pipeline* pipeline,
+                                   const float* amps_raw, const float* hd_raw,
+                                   const float* f0_hz, const float* mags_raw,
+                                   uint64_t seed, uint64_t offset, float* audio,
+                                   int B, int n_chunks, float sample_rate,
+                                   int amp_method, int harmonic_flags,
+                                   int window_size, float initial_bias,
+                                   void* stream);
 
 /* Backward of Harmonic.get_signal w.r.t. the frame-rate harmonic amplitudes
  * ha = amplitudes * harmonic_distribution (the transpose of core.py:1096-1111;

@@ -273,3 +273,25 @@ def test_resample_value_errors():
     core.upsample_with_windows(np.ones([1, 5, 1], np.float32), 15, add_endpoint=False)
   with pytest.raises(ValueError, match='is invalid'):
     core.resample(np.ones([1, 5, 1], np.float32), 10, method='bogus')
+
+
+def test_host_pipeline_validates_without_a_gpu():
+  """ddsp_b200_host_pipeline_*: argument errors come back as status codes before
+  any CUDA call; a null handle is rejected by the forward entry point."""
+  import ctypes
+  lib = _lib.load()
+  h = ctypes.c_void_p()
+  assert lib.ddsp_b200_host_pipeline_create(ctypes.byref(h), 0, 10, 4, 5, 640, 2) == _lib.E_INVALID
+  assert not h.value
+  assert lib.ddsp_b200_decoder_forward_host(None, 1, 1, 1, 1, 0, 0, 1, 1, 1, 16000.0,
+                                            0, 3, 0, -5.0, None) == _lib.E_INVALID
+  assert b'null handle' in lib.ddsp_b200_last_error()
+  assert lib.ddsp_b200_host_pipeline_destroy(None) == 0
+
+
+def test_host_decoder_rejects_non_decoder_dags():
+  import ddsp_b200
+  harm = ddsp_b200.Harmonic(n_samples=640)
+  group = ddsp_b200.ProcessorGroup(dag=[(harm, ['a', 'h', 'f'])])
+  with pytest.raises(ValueError):
+    ddsp_b200.HostDecoder(group, 2, 10, 4, 5)
