@@ -10,6 +10,7 @@
 #include "controls.cuh"
 #include "harmonic.cuh"
 #include "harmonic_fast.cuh"
+#include "harmonic_v2.cuh"
 #include "noise.cuh"
 #include "noise_fused.cuh"
 #include "noise_pipe.cuh"
@@ -56,6 +57,18 @@ static int set_smem(K kernel, size_t bytes, const char* name) {
 }  // namespace ddsp
 
 using namespace ddsp;
+
+namespace ddsp {
+// v2 is the product kernel; DDSP_B200_HARM_IMPL=fast selects the first-generation
+// kernel for A/B measurements (tools/harm_sweep.py).
+static inline int launch_harmonic_best(const HarmonicParams& p, cudaStream_t st) {
+  static const bool use_fast = [] {
+    const char* e = getenv("DDSP_B200_HARM_IMPL");
+    return e != nullptr && strcmp(e, "fast") == 0;
+  }();
+  return use_fast ? launch_harmonic_fast(p, st) : launch_harmonic_v2(p, st);
+}
+}  // namespace ddsp
 
 extern "C" {
 
@@ -132,7 +145,7 @@ int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
   cudaStream_t st = (cudaStream_t)stream;
 
   if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_fast_supported(p)) {
-    int rc = launch_harmonic_fast(p, st);
+    int rc = launch_harmonic_best(p, st);
     if (rc != 1) return rc;   // 1 = declined, fall through to the generic path
   }
 
@@ -405,7 +418,7 @@ static int decoder_forward_impl(const float* amps_raw, const float* hd_raw,
                "decoder_forward: shape outside the fused decoder path "
                "(needs hop %% 64 == 0, n_frequencies <= %d)", kNfMaxNb);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_harmonic_fast(p, st);
+  int rc = launch_harmonic_best(p, st);
   if (rc == 1) {
     set_error("decoder_forward: harmonic tile does not fit shared memory");
     return DDSP_B200_E_UNSUPPORTED;

@@ -15,7 +15,10 @@
 //
 // All geometry is compile-time here; every other shape takes noise_fused.cuh.
 #pragma once
+#include <string.h>
+
 #include "noise_fused.cuh"
+#include "noise_ring.cuh"
 
 namespace ddsp {
 
@@ -455,6 +458,15 @@ inline int launch_noise_best(const float* mags, const float* noise, uint64_t see
                              int N, int window_size, int accumulate,
                              cudaStream_t st, int raw = 0, float bias = 0.f,
                             int item_base = 0) {
+  // noise_ring is the product kernel for the decoder shape; DDSP_B200_NOISE_IMPL
+  // = pipe selects the second-generation kernel for A/B measurements.
+  static const bool use_pipe = [] {
+    const char* e = getenv("DDSP_B200_NOISE_IMPL");
+    return e != nullptr && strcmp(e, "pipe") == 0;
+  }();
+  if (!use_pipe && noise_ring_supported(F, nb, N, window_size))
+    return launch_noise_ring(mags, noise, seed, offset, audio, B, F, N, accumulate,
+                             st, raw, bias, item_base);
   if (noise_pipe_supported(F, nb, N, window_size))
     return launch_noise_pipe(mags, noise, seed, offset, audio, B, F, N, accumulate,
                              st, raw, bias, item_base);

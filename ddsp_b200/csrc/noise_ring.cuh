@@ -1,0 +1,589 @@
+// noise_ring: FilteredNoise.get_signal for the decoder shape (n_frequencies = 65,
+// frame = 64 samples, 128-tap IR; ae.gin:60-68), third generation.  Same maths as
+// noise_fused.cuh / noise_pipe.cuh (windowed zero-phase IR per frame by E/O cosine
+// sums, Philox noise, time-varying FIR == the reference's framed FFT convolution
+// + overlap-add + crop, core.py:1382-1473); the second generation was bound by
+// shared-memory bandwidth (67 % of LSU wavefronts at 47 % FMA-pipe utilisation,
+// profiles/r01_ncu_summary_v7.txt) and by consumer warps marching in lock step
+// through an overlap-add buffer.  What changed:
+//
+//   * GATHER FORM, NO OVERLAP-ADD.  out[64 q + n] = sum_i x_q[i] h_q[n + 62 - i]
+//     + sum_i x_{q+1}[i] h_{q+1}[n - 2 - i] + sum_i x_{q-1}[i] h_{q-1}[n + 126 - i]
+//     (+ x_{q-2}[63] h_{q-2}[127] for n = 0), taps outside [0, 128) being zero:
+//     exactly 128 MACs per output.  A lane owns output frame q and reads the rows
+//     of frames q-2 .. q+1; a warp finishes its 32 x 32 output block in registers
+//     and writes it straight to HBM (st / red.add for the fused Add) - consumer
+//     warps never talk to each other.
+//   * ROW RING, NO HALO.  A persistent CTA walks a contiguous range of frames; the
+//     impulse responses and noise rows live in a ring of 32-row slots in shared
+//     memory (lane-private rows, strides = 2 mod 4 floats: conflict-free LDS.64),
+//     so neighbouring tiles share their edge rows instead of recomputing them.
+//   * ONE WINDOW, TWO ACCUMULATOR SETS.  For an even input x[i] the tap pair
+//     (h[m], h[m+1]) feeds the output pair (n, n+1); for the odd input x[i+1] the
+//     SAME pair feeds (n+1, n+2).  Set A holds pairs (n, n+1), set B pairs
+//     (n+1, n+2): every MAC is an FFMA2 on one 16-pair register window, one IR
+//     copy in shared memory, 2 LDS.64 per 33 FFMA2 (was 3 per 16).
+//   * TRIANGULAR TRIMMING at compile time: the rows of frames q+1 and q-1 cover
+//     complementary triangles of the (n, i) square; fully unrolled bodies skip the
+//     pairs whose taps are all out of range.
+//   * producers: two groups of 4 warps alternate tiles; a group takes its tile
+//     from raw magnitudes (TMA) through exp_sigmoid, both cosine half-sums (in
+//     registers as FFMA2, no exchange) and the windowed taps to the Philox rows.
+#pragma once
+#include "noise_fused.cuh"
+
+namespace ddsp {
+
+namespace nr_ {
+constexpr int NB = 65, FRAME = 64, S = 128, S0 = 128, Q = 32, QP = 36;
+constexpr int NE = 33, NO = 32, SHIFT = 64;
+constexpr int CONS_WARPS = 8, PROD_WARPS = 8;
+constexpr int SLOTS = CONS_WARPS / 2 + 3;          // 32-row slots in the ring: the
+// consumer pairs hold NPAIR + 1 of them, each producer group fills one more
+constexpr int RING = 32 * SLOTS;
+constexpr int THREADS = 32 * (CONS_WARPS + PROD_WARPS);
+constexpr int CONS_REGS = 160, PROD_REGS = 96;   // 256 threads each: 64 K registers
+constexpr int HPAD = 2, HS = 134, XS = 66, MS = 65;   // row strides (floats)
+constexpr int NQ = FRAME / 4;
+
+struct Smem {
+  float te[NE * QP];
+  float to[NO * QP];
+  float win[S];
+  float m[2][32 * MS + 3];
+  alignas(16) float raw[2][32 * NB + 8];
+  alignas(16) float h[RING * HS];
+  alignas(16) float x[RING * XS];
+  alignas(8) unsigned long long full[SLOTS], empty[SLOTS], rawbar[2];
+};
+
+struct Params {
+  const float* __restrict__ mags;
+  const float* __restrict__ noise;
+  float* audio;
+  uint64_t seed, offset;
+  int B, F, N, accumulate, raw, item_base;
+  float bias;
+};
+
+// A contiguous run of output frames [s0, s0 + len) of batch item b.
+struct Seg {
+  int b, s0, len, nP, nC;
+};
+
+__device__ __forceinline__ bool next_seg(long long& g, long long g1, int F, Seg& sg) {
+  if (g >= g1) return false;
+  sg.b = (int)(g / F);
+  sg.s0 = (int)(g - (long long)sg.b * F);
+  sg.len = (int)min((long long)(F - sg.s0), g1 - g);
+  sg.nP = (sg.len + 3 + 31) >> 5;       // production tiles: rows s0-2 .. s0+len
+  sg.nC = (sg.len + 31) >> 5;           // consumption tiles
+  g += sg.len;
+  return true;
+}
+
+__device__ __forceinline__ void mbar_arrive_n(void* bar, int n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(n)
+               : "memory");
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c,
+                                           float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a),
+               "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// ---- consumer: FIR bodies ---------------------------------------------------
+// Window convention: at step e (inputs 2e, 2e+1) W[(c - e) & 15] = (h[m], h[m+1])
+// with m = N0 + 2c + C - 2e: the tap pair that takes x[2e] to outputs (N0+2c,
+// N0+2c+1) [set A] and x[2e+1] to (N0+2c+1, N0+2c+2) [set B].  Bm1 is set B's
+// pair c = -1 (outputs N0-1, N0): at step e it takes x[2e-1] with W_e[0].
+struct Acc {
+  float2 A[16], B[16], Bm1;
+};
+
+// The FIR of one output block runs as a short PROGRAM of 16-step bodies, executed
+// by a loop with a switch so that each body exists once in the instruction stream
+// (fully inlined per call site the consumer code was 80 KB and the warps stalled
+// on instruction fetch, ncu "no_instruction" 3.6 - profiles/r01_ncu_ring1.txt).
+// A body walks 16 steps k = 0..15 of one row: inputs xp[2k], xp[2k+1]; the tap
+// pair of (c, k) sits at hp + 2c - 2k.
+//   FULL : every pair (c, k) matters.
+//   LOWER: only c >= k + 1 (taps left of the row start are zero), 15 steps, no
+//          new pair ever enters the window.
+//   UPPER: only c <= k (taps right of the row end are zero); the window fills up
+//          from pair 0.
+enum { OP_FULL = 0, OP_LOWER = 1, OP_UPPER = 2 };
+struct Op {
+  const float* xp;
+  const float* hp;
+  int kind;
+  int preload;      // 0: window continues, 1: load all 16 pairs, 2: pair 0 only
+  int set_xo;       // xo_prev := xo before the body
+  float xo;
+  int final_op;     // afterwards: Bm1 += xo_prev * W_16[0]  (the last odd input)
+};
+
+// Op i (0..4) of the block program.  x_m1 / h_m1: rows of frame q+1 (tap offset
+// C = -2); x_0 / h_0: frame q (C = 62); x_p1 / h_p1: frame q-1 (C = 126).  h_*
+// point at tap 0; N0 = 0 or 32.
+__device__ __forceinline__ Op block_op(int i, int N0, const float* x_m1,
+                                       const float* h_m1, const float* x_0,
+                                       const float* h_0, const float* x_p1,
+                                       const float* h_p1) {
+  // frame q: all 64 inputs, every pair valid.  The closing op (x[63] with taps
+  // (N0 - 2, N0 - 1)) is all padding for N0 = 0.
+  if (i == 0) return Op{x_0, h_0 + N0 + 62, OP_FULL, 1, 1, 0.f, 0};
+  if (i == 1) return Op{x_0 + 32, h_0 + N0 + 30, OP_FULL, 0, 0, 0.f, N0 != 0};
+  if (N0 == 0) {
+    // frame q+1 reaches outputs n >= i + 2 only (steps 0..14); frame q-1 covers
+    // i >= n - 1: a growing triangle over steps 0..15, then everything
+    if (i == 2) return Op{x_m1, h_m1 - 2, OP_LOWER, 1, 0, 0.f, 0};
+    if (i == 3) return Op{x_p1, h_p1 + 126, OP_UPPER, 2, 1, 0.f, 0};
+    return Op{x_p1 + 32, h_p1 + 94, OP_FULL, 0, 0, 0.f, 1};
+  }
+  // frame q+1: steps 0..15 everything, 16..30 the shrinking triangle; frame q-1:
+  // steps 16..31 the growing triangle, entered with x[31] -> output 32
+  if (i == 2) return Op{x_m1, h_m1 + 30, OP_FULL, 1, 1, 0.f, 0};
+  if (i == 3) return Op{x_m1 + 32, h_m1 - 2, OP_LOWER, 0, 0, 0.f, 0};
+  return Op{x_p1 + 32, h_p1 + 126, OP_UPPER, 2, 1, x_p1[31], 1};
+}
+
+__device__ __forceinline__ void consume_block(Acc& a, int N0, const float* x_m1,
+                                              const float* h_m1, const float* x_0,
+                                              const float* h_0, const float* x_p1,
+                                              const float* h_p1) {
+  float2 W[16];
+  float xo_prev = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < 5; ++i) {
+    const Op op = block_op(i, N0, x_m1, h_m1, x_0, h_0, x_p1, h_p1);
+    const float* __restrict__ xp = op.xp;
+    const float* __restrict__ hp = op.hp;
+    if (op.preload == 1) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) W[c] = *reinterpret_cast<const float2*>(hp + 2 * c);
+    } else if (op.preload == 2) {
+      W[0] = *reinterpret_cast<const float2*>(hp);
+    }
+    if (op.set_xo) xo_prev = op.xo;
+    switch (op.kind) {
+      case OP_FULL:
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 xv = *reinterpret_cast<const float2*>(xp + 2 * k);
+          // pair 15 first: its slot is refilled (for step k + 1) right behind it
+          a.A[15] = nf_ffma2(xv.x, W[(15 - k) & 15], a.A[15]);
+          a.B[15] = nf_ffma2(xv.y, W[(15 - k) & 15], a.B[15]);
+          const float2 wn = *reinterpret_cast<const float2*>(hp - 2 * (k + 1));
+#pragma unroll
+          for (int c = 14; c >= 0; --c) {
+            a.A[c] = nf_ffma2(xv.x, W[(c - k) & 15], a.A[c]);
+            a.B[c] = nf_ffma2(xv.y, W[(c - k) & 15], a.B[c]);
+          }
+          a.Bm1 = nf_ffma2(xo_prev, W[(0 - k) & 15], a.Bm1);
+          W[(15 - k) & 15] = wn;
+          xo_prev = xv.y;
+        }
+        break;
+      case OP_LOWER:
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+          const float2 xv = *reinterpret_cast<const float2*>(xp + 2 * k);
+#pragma unroll
+          for (int c = 15; c >= k + 1; --c) {
+            a.A[c] = nf_ffma2(xv.x, W[(c - k) & 15], a.A[c]);
+            a.B[c] = nf_ffma2(xv.y, W[(c - k) & 15], a.B[c]);
+          }
+          xo_prev = xv.y;
+        }
+        break;
+      default:
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 xv = *reinterpret_cast<const float2*>(xp + 2 * k);
+          const float2 wn = *reinterpret_cast<const float2*>(hp - 2 * (k + 1));
+#pragma unroll
+          for (int c = k; c >= 0; --c) {
+            a.A[c] = nf_ffma2(xv.x, W[(c - k) & 15], a.A[c]);
+            a.B[c] = nf_ffma2(xv.y, W[(c - k) & 15], a.B[c]);
+          }
+          a.Bm1 = nf_ffma2(xo_prev, W[(0 - k) & 15], a.Bm1);
+          W[(15 - k) & 15] = wn;
+          xo_prev = xv.y;
+        }
+        break;
+    }
+    if (op.final_op) a.Bm1 = nf_ffma2(xo_prev, W[0], a.Bm1);
+  }
+}
+
+__global__ void __launch_bounds__(nr_::THREADS, 1)
+noise_ring_kernel(Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float invS0 = 1.0f / (float)S0;
+
+  // ---- once: tables, window, zeroed ring (pads stay zero), barriers ----
+  for (int e = tid; e < NE * QP; e += THREADS) {
+    const int k = e / QP, n = e - k * QP;
+    const int ph = (2 * k * n) % S0;
+    const float ck = (k == 0 || 2 * k == NB - 1) ? invS0 : 2.0f * invS0;
+    sm.te[e] = (n <= Q) ? ck * cospif(2.0f * (float)ph * invS0) : 0.f;
+  }
+  for (int e = tid; e < NO * QP; e += THREADS) {
+    const int k = e / QP, n = e - k * QP;
+    const int ph = ((2 * k + 1) * n) % S0;
+    sm.to[e] = (n < Q) ? 2.0f * invS0 * cospif(2.0f * (float)ph * invS0) : 0.f;
+  }
+  for (int j = tid; j < S; j += THREADS)
+    sm.win[j] = 0.5f - 0.5f * cospif(2.0f * (float)j / (float)S0);   // core.py:1498,1515
+  for (int e = tid; e < RING * HS; e += THREADS) sm.h[e] = 0.f;
+  for (int e = tid; e < RING * XS; e += THREADS) sm.x[e] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < SLOTS; ++i) {
+      mbar_init(&sm.full[i], 4);
+      mbar_init(&sm.empty[i], 4);
+    }
+    mbar_init(&sm.rawbar[0], 1);
+    mbar_init(&sm.rawbar[1], 1);
+  }
+  __syncthreads();
+
+  // this CTA's frames: an even share of the B * F frames, cut at item boundaries
+  const long long T = (long long)p.B * p.F;
+  const long long g_lo = T * blockIdx.x / gridDim.x;
+  const long long g_hi = T * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp < CONS_WARPS) {
+    // =========================== CONSUMERS ===================================
+    // (two warpgroups; the FIR wants ~150 registers: take them from the producers)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
+    const int pair = warp >> 1, half = warp & 1;
+    constexpr int NPAIR = CONS_WARPS / 2;
+    long long g = g_lo;
+    Seg sg;
+    int pbase = 0, ct = 0;
+    while (next_seg(g, g_hi, p.F, sg)) {
+      for (int t = 0; t < sg.nC; ++t, ++ct) {
+        if ((ct % NPAIR) != pair) continue;
+        // rows of this tile live in production tiles t and t+1 of the segment
+        // (two producer groups finish tiles out of order: wait for both)
+        {
+          const int P0 = pbase + t, P1 = pbase + min(t + 1, sg.nP - 1);
+          mbar_wait(&sm.full[P0 % SLOTS], (P0 / SLOTS) & 1);
+          mbar_wait(&sm.full[P1 % SLOTS], (P1 / SLOTS) & 1);
+        }
+        const int q_rel = 32 * t + lane;                // output frame, relative
+        // lanes past the end of the segment redo its last frame (and store
+        // nothing): they must not wander into rows nobody produced
+        const int rho = min(q_rel, sg.len - 1) + 2;     // its production row
+        const int rbase = pbase * 32;
+        auto xrow = [&](int r) { return sm.x + ((rbase + r) % RING) * XS; };
+        auto hrow = [&](int r) { return sm.h + ((rbase + r) % RING) * HS + HPAD; };
+        Acc a;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a.A[c] = a.B[c] = make_float2(0.f, 0.f);
+        a.Bm1 = make_float2(0.f, 0.f);
+        consume_block(a, 32 * half, xrow(rho + 1), hrow(rho + 1), xrow(rho), hrow(rho),
+                      xrow(rho - 1), hrow(rho - 1));
+        // frame q-2 reaches output 0 only: input 63 through tap 127
+        if (half == 0)
+          a.A[0].x = fmaf(xrow(rho - 2)[63], hrow(rho - 2)[127], a.A[0].x);
+        __syncwarp();
+        if (lane == 0) {
+          // release the slots: a production tile is read by consumption tiles
+          // tau-1 and tau (two warps each); a lone reader arrives twice.
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            const int tau = t + d;
+            if (tau < sg.nP) {
+              const int readers = (tau >= 1 ? 1 : 0) + (tau < sg.nC ? 1 : 0);
+              mbar_arrive_n(&sm.empty[(pbase + tau) % SLOTS], 2 / readers);
+            }
+          }
+        }
+        // ---- store / accumulate the 32 outputs of this lane's frame ----
+        if (q_rel < sg.len) {
+          float* o = p.audio + (size_t)sg.b * p.N + (size_t)(sg.s0 + q_rel) * FRAME +
+                     32 * half;
+          float v[32];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float2 bp = (c == 0) ? a.Bm1 : a.B[c - 1];
+            v[2 * c] = a.A[c].x + bp.y;
+            v[2 * c + 1] = a.A[c].y + a.B[c].x;
+          }
+          const long long t0 = (long long)(sg.s0 + q_rel) * FRAME + 32 * half;
+          if (t0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (p.accumulate)
+                red_add_v4(o + 4 * u, v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+              else
+                *reinterpret_cast<float4*>(o + 4 * u) =
+                    make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+              if (t0 + u < p.N) {
+                if (p.accumulate) o[u] += v[u]; else o[u] = v[u];
+              }
+            }
+          }
+        }
+      }
+      pbase += sg.nP;
+    }
+  } else {
+    // =============================== PRODUCERS ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
+    // Two groups of four warps; group g builds the production tiles P = g (mod 2)
+    // end to end: magnitudes (TMA) -> exp_sigmoid -> both cosine half-sums ->
+    // windowed taps, then the tile's noise rows.  A group has a whole tile-pair
+    // period for one tile, so its latency chains (TMA, MUFU, LDS) stay off the
+    // consumers' critical path.
+    const int grp = (warp - CONS_WARPS) >> 2;         // 0 / 1
+    const int iw = (warp - CONS_WARPS) & 3;           // column block / slice
+    const int ptid = tid - (CONS_WARPS + 4 * grp) * 32;   // 0..127 within the group
+    constexpr int PT = 128;
+    const int bar_id = 1 + grp;
+    float* s_raw = sm.raw[grp];
+    float* s_m = sm.m[grp];
+    void* rawbar = &sm.rawbar[grp];
+    const float* mags_end = p.mags + (size_t)p.B * p.F * NB;
+    // Raw magnitudes of a production tile -> s_raw (asynchronously; consumed one
+    // of the group's tiles later).  The valid rows are contiguous in HBM: ONE TMA
+    // bulk copy of the enclosing 16-byte aligned span (rows are only 4-byte
+    // aligned: 65 floats); row r lands at s_raw[roff + 65 r].  Spans that would
+    // leave the tensor fall back to per-element cp.async.
+    auto prefetch = [&](const Seg& s, int tau) -> int {
+      const int jb = s.s0 - 2 + 32 * tau;
+      const int r_lo = max(0, -jb), r_hi = min(32, p.F - jb);
+      if (r_hi <= r_lo) {
+        if (ptid == 0) mbar_arrive(rawbar);
+        return 0;
+      }
+      const float* src = p.mags + ((size_t)s.b * p.F + jb + r_lo) * NB;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+      const int off = (int)((a & 15) >> 2);
+      const uint32_t bytes = (uint32_t)(((off + (r_hi - r_lo) * NB) * 4 + 15) & ~15);
+      const uintptr_t a_al = a & ~(uintptr_t)15;
+      if (a_al >= reinterpret_cast<uintptr_t>(p.mags) &&
+          a_al + bytes <= reinterpret_cast<uintptr_t>(mags_end)) {
+        if (ptid == 0) {
+          mbar_expect_tx(rawbar, bytes);
+          tma_bulk_g2s(s_raw, reinterpret_cast<const void*>(a_al), bytes, rawbar);
+        }
+        return off - r_lo * NB;
+      }
+      for (int e = ptid; e < (r_hi - r_lo) * NB; e += PT) cp_async4(s_raw + e, src + e);
+      cp_async_wait_all();
+      named_bar(bar_id, PT);
+      if (ptid == 0) mbar_arrive(rawbar);
+      return -r_lo * NB;
+    };
+    // iterator over the CTA's production tiles: (segment, tau), global index P
+    struct It {
+      long long g;     // frames consumed by next_seg so far
+      Seg sg;
+      int tau, P;
+      bool ok;
+    };
+    auto it_begin = [&]() {
+      It it;
+      it.g = g_lo; it.tau = 0; it.P = 0;
+      it.ok = next_seg(it.g, g_hi, p.F, it.sg);
+      return it;
+    };
+    auto it_next = [&](It& it) {
+      ++it.P;
+      if (++it.tau >= it.sg.nP) {
+        it.tau = 0;
+        it.ok = next_seg(it.g, g_hi, p.F, it.sg);
+      }
+    };
+    It cur = it_begin();
+    if (grp == 1 && cur.ok) it_next(cur);
+    int roff = 0;
+    if (cur.ok) roff = prefetch(cur.sg, cur.tau);
+    int n_mine = 0;                                   // tiles this group has staged
+    while (cur.ok) {
+      It nxt = cur;
+      it_next(nxt);
+      if (nxt.ok) it_next(nxt);
+      const Seg& sg = cur.sg;
+      const int P = cur.P, slot = P % SLOTS;
+      const int jb = sg.s0 - 2 + 32 * cur.tau;
+      // A. magnitudes -> lane-private rows (exp_sigmoid fused, synths.py:176-177)
+      mbar_wait(rawbar, n_mine & 1);
+      named_bar(bar_id, PT);       // the group is done reading s_m (previous tile)
+      {
+        const int j = jb + lane;
+        const bool ok = (j >= 0 && j < p.F);
+        const int k0 = iw * 17;
+        const float* src = s_raw + roff + lane * NB + k0;
+        float* dst = s_m + lane * MS + k0;
+        float v[17];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) v[k] = (ok && k0 + k < NB) ? src[k] : 0.f;
+        if (p.raw) {
+#pragma unroll
+          for (int k = 0; k < 17; ++k) v[k] = exp_sigmoid_f(v[k] + p.bias);
+        }
+#pragma unroll
+        for (int k = 0; k < 17; ++k)
+          if (k0 + k < NB) dst[k] = ok ? v[k] : 0.f;
+      }
+      named_bar(bar_id, PT);       // s_raw consumed, s_m complete
+      if (nxt.ok) roff = prefetch(nxt.sg, nxt.tau);
+      ++n_mine;
+      // wait until the consumers have drained this slot
+      if (P >= SLOTS) mbar_wait(&sm.empty[slot], ((P / SLOTS) - 1) & 1);
+      // B. both half-size cosine sums of 8 columns (9 for the last block):
+      //    h0[n] = E[n] + O[n], h0[64 - n] = E[n] - O[n]   
+      {
+        const int n0 = 8 * iw;
+        float2 aE[4], aO[4];
+        float e8 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) aE[c] = aO[c] = make_float2(0.f, 0.f);
+        const float* mrow = s_m + lane * MS;
+#pragma unroll 4
+        for (int k = 0; k < NO; ++k) {
+          const float me = mrow[2 * k], mo = mrow[2 * k + 1];
+          const float4* tE = reinterpret_cast<const float4*>(sm.te + k * QP + n0);
+          const float4* tO = reinterpret_cast<const float4*>(sm.to + k * QP + n0);
+          const float4 e0 = tE[0], e1 = tE[1], o0 = tO[0], o1 = tO[1];
+          aE[0] = nf_ffma2(me, make_float2(e0.x, e0.y), aE[0]);
+          aE[1] = nf_ffma2(me, make_float2(e0.z, e0.w), aE[1]);
+          aE[2] = nf_ffma2(me, make_float2(e1.x, e1.y), aE[2]);
+          aE[3] = nf_ffma2(me, make_float2(e1.z, e1.w), aE[3]);
+          aO[0] = nf_ffma2(mo, make_float2(o0.x, o0.y), aO[0]);
+          aO[1] = nf_ffma2(mo, make_float2(o0.z, o0.w), aO[1]);
+          aO[2] = nf_ffma2(mo, make_float2(o1.x, o1.y), aO[2]);
+          aO[3] = nf_ffma2(mo, make_float2(o1.z, o1.w), aO[3]);
+          if (iw == 3) e8 = fmaf(me, sm.te[k * QP + Q], e8);
+        }
+        {
+          const float me = mrow[2 * NO];               // k = 32: even terms only
+          const float4* tE = reinterpret_cast<const float4*>(sm.te + NO * QP + n0);
+          const float4 e0 = tE[0], e1 = tE[1];
+          aE[0] = nf_ffma2(me, make_float2(e0.x, e0.y), aE[0]);
+          aE[1] = nf_ffma2(me, make_float2(e0.z, e0.w), aE[1]);
+          aE[2] = nf_ffma2(me, make_float2(e1.x, e1.y), aE[2]);
+          aE[3] = nf_ffma2(me, make_float2(e1.z, e1.w), aE[3]);
+          if (iw == 3) e8 = fmaf(me, sm.te[NO * QP + Q], e8);
+        }
+        float* hr = sm.h + (slot * 32 + lane) * HS + HPAD;
+        const float E[8] = {aE[0].x, aE[0].y, aE[1].x, aE[1].y,
+                            aE[2].x, aE[2].y, aE[3].x, aE[3].y};
+        const float O[8] = {aO[0].x, aO[0].y, aO[1].x, aO[1].y,
+                            aO[2].x, aO[2].y, aO[3].x, aO[3].y};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int n = n0 + c;
+          const float hp = E[c] + O[c];                // |offset| = n
+          const float hm = E[c] - O[c];                // |offset| = 64 - n
+          hr[SHIFT + n] = sm.win[SHIFT + n] * hp;
+          if (n != 0) hr[SHIFT - n] = sm.win[SHIFT - n] * hp;
+          if (n != 0) hr[S - n] = sm.win[S - n] * hm;  // tap 64 + (64 - n)
+          hr[n] = sm.win[n] * hm;                      // tap 64 - (64 - n)
+        }
+        if (iw == 3) {                                 // n = 32: O[32] = 0
+          hr[SHIFT + Q] = sm.win[SHIFT + Q] * e8;
+          hr[SHIFT - Q] = sm.win[SHIFT - Q] * e8;
+        }
+      }
+      // C. the tile's noise rows: 512 quads, 128 per warp
+      {
+        const float* nzb = p.noise ? p.noise + (size_t)sg.b * p.N : nullptr;
+        const uint32_t item = (uint32_t)(sg.b + p.item_base);
+        float* xs = sm.x + slot * 32 * XS;
+        const long long p_lo = (long long)jb * FRAME;
+        const bool interior = (jb >= 0) && (jb + 32 <= p.F) &&
+                              (p_lo + 32ll * FRAME <= p.N) && !nzb;
+        constexpr int PER = 32 * NQ / 4;               // 128 quads per warp
+        if (interior) {
+          const uint32_t qbase = (uint32_t)(p_lo >> 2);
+#pragma unroll
+          for (int it = 0; it < PER / 32; ++it) {
+            const int e = iw * PER + it * 32 + lane;
+            const int r = e >> 4, qd = e & 15;
+            const float4 v = noise4(qbase + (uint32_t)e, item, p.seed, p.offset);
+            float2* d = reinterpret_cast<float2*>(xs + r * XS + 4 * qd);
+            d[0] = make_float2(v.x, v.y);
+            d[1] = make_float2(v.z, v.w);
+          }
+        } else {
+          for (int it = 0; it < PER / 32; ++it) {
+            const int e = iw * PER + it * 32 + lane;
+            const int r = e >> 4, qd = e & 15;
+            const int j = jb + r;
+            const long long pp = (long long)j * FRAME + 4 * qd;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (j >= 0 && j < p.F && pp < p.N) {
+              if (nzb) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (pp + u < p.N) v[u] = nzb[pp + u];
+              } else {
+                const float4 r4 = noise4((uint32_t)(pp >> 2), item, p.seed, p.offset);
+                v[0] = r4.x;
+                if (pp + 1 < p.N) v[1] = r4.y;
+                if (pp + 2 < p.N) v[2] = r4.z;
+                if (pp + 3 < p.N) v[3] = r4.w;
+              }
+            }
+            float2* d = reinterpret_cast<float2*>(xs + r * XS + 4 * qd);
+            d[0] = make_float2(v[0], v[1]);
+            d[1] = make_float2(v[2], v[3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.full[slot]);
+      cur = nxt;
+    }
+  }
+}
+
+}  // namespace nr_
+
+inline bool noise_ring_supported(int F, int nb, int N, int window_size) {
+  if (nb != nr_::NB) return false;
+  if (N % F != 0 || N / F != nr_::FRAME) return false;
+  IrGeom g = make_ir_geom(nb, window_size);
+  return !g.padded && g.S == nr_::S;
+}
+
+inline int launch_noise_ring(const float* mags, const float* noise, uint64_t seed,
+                             uint64_t offset, float* audio, int B, int F, int N,
+                             int accumulate, cudaStream_t st, int raw, float bias,
+                             int item_base) {
+  nr_::Params p;
+  p.mags = mags; p.noise = noise; p.audio = audio; p.seed = seed; p.offset = offset;
+  p.B = B; p.F = F; p.N = N; p.accumulate = accumulate; p.raw = raw; p.bias = bias;
+  p.item_base = item_base;
+  const long long T = (long long)B * F;
+  const size_t smem = sizeof(nr_::Smem);
+  static_assert(sizeof(nr_::Smem) <= 227 * 1024, "noise_ring shared memory");
+  cudaError_t e = cudaFuncSetAttribute(
+      nr_::noise_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("filtered_noise_forward: cannot reserve %zu B smem: %s", smem,
+              cudaGetErrorString(e));
+    return DDSP_B200_E_CUDA;
+  }
+  // one persistent CTA per SM; tiny workloads get one CTA per 32-frame tile
+  const int grid = (int)std::max<long long>(
+      1, std::min<long long>((long long)kNumSMs, (T + 31) / 32));
+  nr_::noise_ring_kernel<<<grid, nr_::THREADS, smem, st>>>(p);
+  DDSP_CHECK_LAUNCH("filtered_noise_forward(ring)");
+  return 0;
+}
+
+}  // namespace ddsp

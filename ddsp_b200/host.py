@@ -19,6 +19,41 @@ from ddsp_b200 import _lib
 from ddsp_b200 import core
 
 
+def _cpulist(text):
+  cpus = set()
+  for part in text.strip().split(','):
+    if not part:
+      continue
+    lo, _, hi = part.partition('-')
+    cpus.update(range(int(lo), int(hi or lo) + 1))
+  return cpus
+
+
+def bind_to_device_numa_node(device=None):
+  """Pins the calling thread to the CPUs of the NUMA node the GPU hangs off
+  (Linux sysfs), so that page-locked buffers allocated afterwards are first
+  touched - and therefore placed - in memory local to the GPU's PCIe root.  On a
+  two-socket host a pinned buffer on the far socket costs the host->device copies
+  up to half their bandwidth.  Returns the node id, or None when the topology
+  cannot be read (nothing is changed then)."""
+  import os
+  try:
+    index = torch.cuda.current_device() if device is None else torch.device(device).index
+    prop = torch.cuda.get_device_properties(index)
+    bus = '%04x:%02x:%02x.0' % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+    node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+    if node < 0:
+      return None
+    cpus = _cpulist(open('/sys/devices/system/node/node%d/cpulist' % node).read())
+    cpus &= os.sched_getaffinity(0)
+    if not cpus:
+      return None
+    os.sched_setaffinity(0, cpus)
+    return node
+  except (OSError, ValueError, AttributeError, RuntimeError):
+    return None
+
+
 def pinned_empty(shape):
   """Page-locked float32 host tensor (asynchronous copies need pinned memory)."""
   return torch.empty(tuple(shape), dtype=torch.float32).pin_memory()
