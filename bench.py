@@ -296,7 +296,7 @@ def run_ours(args):
   # The PCIe link and copy engines need ~50 ms of traffic to reach full speed
   # after idling (first copies of a run move at about half rate): warm them up,
   # then pick the chunk count on this box (rank-local, short) before timing.
-  cand = [args.chunks] if args.chunks > 0 else [2, 4, 8]
+  cand = [args.chunks] if args.chunks > 0 else [2, 3, 4]
   decs = {c: ddsp_b200.HostDecoder(group, max_batch=B, n_frames=N_FRAMES,
                                    n_harmonics=N_HARM, n_bands=N_BANDS, n_chunks=c)
           for c in cand}
@@ -482,7 +482,7 @@ def _main():
                   help='batch items per GPU (configs[1] = 32)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--chunks', type=int, default=0,
-                  help='chunks of the host-buffer (e2e) pipeline; 0 = pick among 2/4/8')
+                  help='chunks of the host-buffer (e2e) pipeline; 0 = pick among 2/3/4')
   ap.add_argument('--extra', type=int, default=1,
                   help='also time the B=256 (configs[2]) step on rank 0')
   args = ap.parse_args()

@@ -426,7 +426,7 @@ static int decoder_forward_impl(const float* amps_raw, const float* hd_raw,
   if (rc) return rc;
   return launch_noise_best(mags_raw, noise, seed, offset, audio, B, F, nb, N,
                            window_size, /*accumulate=*/1, st, /*raw=*/1,
-                           initial_bias, item_base);
+                           initial_bias, item_base, /*overlap_previous=*/1);
 }
 
 int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
@@ -483,6 +483,8 @@ int ddsp_b200_host_pipeline_create(ddsp_b200_host_pipeline** out, int max_B, int
   hp->d_audio = hp->d_mags + n_mags;
   if ((e = cudaStreamCreateWithFlags(&hp->s_h2d, cudaStreamNonBlocking)) != cudaSuccess)
     return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&hp->s_h2d2, cudaStreamNonBlocking)) != cudaSuccess)
+    return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&hp->s_d2h, cudaStreamNonBlocking)) != cudaSuccess)
     return fail("cudaStreamCreate", e);
   if ((e = cudaEventCreateWithFlags(&hp->ev_start, cudaEventDisableTiming)) != cudaSuccess)
@@ -497,6 +499,10 @@ int ddsp_b200_host_pipeline_create(ddsp_b200_host_pipeline** out, int max_B, int
     if ((e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming)) != cudaSuccess)
       return fail("cudaEventCreate", e);
     hp->ev_comp.push_back(b);
+    cudaEvent_t a2 = nullptr;
+    if ((e = cudaEventCreateWithFlags(&a2, cudaEventDisableTiming)) != cudaSuccess)
+      return fail("cudaEventCreate", e);
+    hp->ev_h2d2.push_back(a2);
   }
   *out = reinterpret_cast<ddsp_b200_host_pipeline*>(hp);
   return 0;
@@ -527,33 +533,58 @@ int ddsp_b200_decoder_forward_host(ddsp_b200_host_pipeline* handle,
   DDSP_REQUIRE(dev == hp->device, DDSP_B200_E_INVALID,
                "decoder_forward_host: pipeline belongs to device %d, current is %d",
                hp->device, dev);
-  n_chunks = std::max(1, std::min(std::min(n_chunks, hp->max_chunks), B));
+  n_chunks = std::max(1, std::min(std::min(std::min(n_chunks, hp->max_chunks), B), 64));
   const int F = hp->F, K = hp->K, nb = hp->nb, N = hp->N;
   cudaStream_t st = (cudaStream_t)stream;
   // Order this call after whatever the caller queued on `st`, and after the
   // previous call's last device->host copy (the staging buffers are reused).
   DDSP_CUDA_TRY(cudaEventRecord(hp->ev_start, st), "decoder_forward_host: event");
   DDSP_CUDA_TRY(cudaStreamWaitEvent(hp->s_h2d, hp->ev_start, 0), "decoder_forward_host: wait");
-  if (hp->used)
+  DDSP_CUDA_TRY(cudaStreamWaitEvent(hp->s_h2d2, hp->ev_start, 0), "decoder_forward_host: wait");
+  if (hp->used) {
     DDSP_CUDA_TRY(cudaStreamWaitEvent(hp->s_h2d, hp->ev_done, 0), "decoder_forward_host: wait");
+    DDSP_CUDA_TRY(cudaStreamWaitEvent(hp->s_h2d2, hp->ev_done, 0), "decoder_forward_host: wait");
+  }
   hp->used = true;
-  const int per = (B + n_chunks - 1) / n_chunks;
-  int c = 0;
-  for (int b0 = 0; b0 < B; b0 += per, ++c) {
-    const int nbi = std::min(per, B - b0);
+  // Two host->device streams (harmonic_distribution on one; magnitudes and the
+  // small per-frame vectors on the other): a copy costs ~10 us of set-up however
+  // small it is, and on one stream those set-ups do not overlap the previous
+  // transfer - two streams keep the link busy while one of them sets up.  The
+  // per-frame vectors go over once for the whole batch.
+  DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_f0, f0_hz, sizeof(float) * (size_t)B * F,
+                                cudaMemcpyHostToDevice, hp->s_h2d2), "decoder_forward_host: H2D f0");
+  DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_amps, amps_raw, sizeof(float) * (size_t)B * F,
+                                cudaMemcpyHostToDevice, hp->s_h2d2), "decoder_forward_host: H2D amps");
+  // Chunk sizes halve: the call ends with the compute + device->host copy of the
+  // LAST chunk (nothing left to overlap them with), so that one should be small,
+  // while few chunks keep the per-chunk submission cost down.
+  int sizes[64];
+  int n_c = 0;
+  for (int b0 = 0; b0 < B; ++n_c) {
+    const int left = B - b0;
+    sizes[n_c] = (n_c == n_chunks - 1 || n_c == 63) ? left : std::max(1, (left + 1) / 2);
+    b0 += sizes[n_c];
+  }
+  // First queue EVERY host->device copy: the copy engines then never wait for
+  // this thread to get through the launches and event calls of earlier chunks
+  // (~35 us of driver time per chunk, longer than a small chunk's transfer).
+  for (int c = 0, b0 = 0; c < n_c; b0 += sizes[c], ++c) {
+    const int nbi = sizes[c];
     const size_t o1 = (size_t)b0 * F;
-    DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_f0 + o1, f0_hz + o1, sizeof(float) * nbi * F,
-                                  cudaMemcpyHostToDevice, hp->s_h2d), "decoder_forward_host: H2D f0");
-    DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_amps + o1, amps_raw + o1, sizeof(float) * nbi * F,
-                                  cudaMemcpyHostToDevice, hp->s_h2d), "decoder_forward_host: H2D amps");
     DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_hd + o1 * K, hd_raw + o1 * K,
                                   sizeof(float) * (size_t)nbi * F * K,
                                   cudaMemcpyHostToDevice, hp->s_h2d), "decoder_forward_host: H2D hd");
+    DDSP_CUDA_TRY(cudaEventRecord(hp->ev_h2d[c], hp->s_h2d), "decoder_forward_host: event");
     DDSP_CUDA_TRY(cudaMemcpyAsync(hp->d_mags + o1 * nb, mags_raw + o1 * nb,
                                   sizeof(float) * (size_t)nbi * F * nb,
-                                  cudaMemcpyHostToDevice, hp->s_h2d), "decoder_forward_host: H2D mags");
-    DDSP_CUDA_TRY(cudaEventRecord(hp->ev_h2d[c], hp->s_h2d), "decoder_forward_host: event");
+                                  cudaMemcpyHostToDevice, hp->s_h2d2), "decoder_forward_host: H2D mags");
+    DDSP_CUDA_TRY(cudaEventRecord(hp->ev_h2d2[c], hp->s_h2d2), "decoder_forward_host: event");
+  }
+  for (int c = 0, b0 = 0; c < n_c; b0 += sizes[c], ++c) {
+    const int nbi = sizes[c];
+    const size_t o1 = (size_t)b0 * F;
     DDSP_CUDA_TRY(cudaStreamWaitEvent(st, hp->ev_h2d[c], 0), "decoder_forward_host: wait");
+    DDSP_CUDA_TRY(cudaStreamWaitEvent(st, hp->ev_h2d2[c], 0), "decoder_forward_host: wait");
     int rc = decoder_forward_impl(hp->d_amps + o1, hp->d_hd + o1 * K, hp->d_f0 + o1,
                                   hp->d_mags + o1 * nb, nullptr, seed, offset,
                                   hp->d_audio + (size_t)b0 * N, nbi, F, K, nb, N,

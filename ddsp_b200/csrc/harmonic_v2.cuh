@@ -282,6 +282,9 @@ harmonic_v2_kernel(HarmonicParams p, int use_tma, int FW) {
   int2* sKc = (int2*)(wbase + L.w_kc);
   int* sLive = (int*)(wbase + L.w_live);
 
+  // Programmatic dependent launch: the next kernel in the stream (the noise
+  // kernel of the decoder) may start its prologue on SMs this grid has vacated.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ---- 0. the frame slab: one TMA bulk copy, issued before anything else ----
   if (use_tma && tid == 0) {
     mbar_init(mbar, 1);
@@ -449,9 +452,12 @@ inline int launch_harmonic_v2(HarmonicParams p, cudaStream_t st) {
   // Frames per warp: 8 amortises the per-warp prologue best; fewer when the grid
   // would not fill the chip a few times over (the CTAs' work varies ~10x with f0,
   // so several waves are needed for the block scheduler to balance it).
+  // (measured, B200: B=256 -> FW 8/16 equal, FW 4 +12 %; B=32 -> FW 4 best, FW 2
+  // and FW 8 +14 % / +9 %)
   int FW = 8;
-  const long long want_ctas = 20ll * kNumSMs;
-  while (FW > 2 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < want_ctas) FW >>= 1;
+  const long long want_ctas = 8ll * kNumSMs;
+  while (FW > 4 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < want_ctas) FW >>= 1;
+  while (FW > 1 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < kNumSMs) FW >>= 1;
   if (env_fw > 0) FW = std::min(32, env_fw);
   FW = std::max(1, std::min(FW, (p.F + NW - 1) / NW));
   while (FW > 1 && smem_layout(FW, p.Kp, p.hop).total > 64 * 1024) FW = (FW + 1) / 2;

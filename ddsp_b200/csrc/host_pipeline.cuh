@@ -7,7 +7,7 @@
 // work: the step costs about max(H2D, compute, D2H) instead of their sum.
 //
 // The handle owns what such a pipeline needs beyond the caller's buffers: one
-// device staging allocation, two streams and the events.  It is the one place
+// device staging allocation, three copy streams and the events.  It is the one place
 // where the library allocates; everything is released by *_destroy.
 #pragma once
 #include <vector>
@@ -22,9 +22,9 @@ struct HostPipeline {
   float* d_base = nullptr;
   float *d_amps = nullptr, *d_hd = nullptr, *d_f0 = nullptr, *d_mags = nullptr,
         *d_audio = nullptr;
-  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_h2d = nullptr, s_h2d2 = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_start = nullptr, ev_done = nullptr;
-  std::vector<cudaEvent_t> ev_h2d, ev_comp;
+  std::vector<cudaEvent_t> ev_h2d, ev_h2d2, ev_comp;
   bool used = false;
 };
 
@@ -35,12 +35,15 @@ inline void host_pipeline_free(HostPipeline* hp) {
     cudaGetDevice(&cur);
     cudaSetDevice(hp->device);
     if (hp->s_h2d) cudaStreamSynchronize(hp->s_h2d);
+    if (hp->s_h2d2) cudaStreamSynchronize(hp->s_h2d2);
     if (hp->s_d2h) cudaStreamSynchronize(hp->s_d2h);
     for (auto e : hp->ev_h2d) cudaEventDestroy(e);
+    for (auto e : hp->ev_h2d2) cudaEventDestroy(e);
     for (auto e : hp->ev_comp) cudaEventDestroy(e);
     if (hp->ev_start) cudaEventDestroy(hp->ev_start);
     if (hp->ev_done) cudaEventDestroy(hp->ev_done);
     if (hp->s_h2d) cudaStreamDestroy(hp->s_h2d);
+    if (hp->s_h2d2) cudaStreamDestroy(hp->s_h2d2);
     if (hp->s_d2h) cudaStreamDestroy(hp->s_d2h);
     if (hp->d_base) cudaFree(hp->d_base);
     cudaSetDevice(cur);

@@ -457,7 +457,7 @@ inline int launch_noise_best(const float* mags, const float* noise, uint64_t see
                              uint64_t offset, float* audio, int B, int F, int nb,
                              int N, int window_size, int accumulate,
                              cudaStream_t st, int raw = 0, float bias = 0.f,
-                            int item_base = 0) {
+                            int item_base = 0, int overlap_previous = 0) {
   // noise_ring is the product kernel for the decoder shape; DDSP_B200_NOISE_IMPL
   // = pipe selects the second-generation kernel for A/B measurements.
   static const bool use_pipe = [] {
@@ -466,7 +466,7 @@ inline int launch_noise_best(const float* mags, const float* noise, uint64_t see
   }();
   if (!use_pipe && noise_ring_supported(F, nb, N, window_size))
     return launch_noise_ring(mags, noise, seed, offset, audio, B, F, N, accumulate,
-                             st, raw, bias, item_base);
+                             st, raw, bias, item_base, overlap_previous);
   if (noise_pipe_supported(F, nb, N, window_size))
     return launch_noise_pipe(mags, noise, seed, offset, audio, B, F, N, accumulate,
                              st, raw, bias, item_base);

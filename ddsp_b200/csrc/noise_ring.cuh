@@ -37,12 +37,14 @@ namespace ddsp {
 namespace nr_ {
 constexpr int NB = 65, FRAME = 64, S = 128, S0 = 128, Q = 32, QP = 36;
 constexpr int NE = 33, NO = 32, SHIFT = 64;
-constexpr int CONS_WARPS = 8, PROD_WARPS = 8;
+constexpr int CONS_WARPS = 8, PROD_GROUPS = 3, PROD_WARPS = 4 * PROD_GROUPS;
 constexpr int SLOTS = CONS_WARPS / 2 + 3;          // 32-row slots in the ring: the
 // consumer pairs hold NPAIR + 1 of them, each producer group fills one more
 constexpr int RING = 32 * SLOTS;
 constexpr int THREADS = 32 * (CONS_WARPS + PROD_WARPS);
-constexpr int CONS_REGS = 160, PROD_REGS = 96;   // 256 threads each: 64 K registers
+// 640 threads launch with 96 registers each; the consumers (256 threads) grow to
+// CONS_REGS out of what the producers (384 threads) give back.
+constexpr int CONS_REGS = 144, PROD_REGS = 64;
 constexpr int HPAD = 2, HS = 134, XS = 66, MS = 65;   // row strides (floats)
 constexpr int NQ = FRAME / 4;
 
@@ -50,11 +52,10 @@ struct Smem {
   float te[NE * QP];
   float to[NO * QP];
   float win[S];
-  float m[2][32 * MS + 3];
-  alignas(16) float raw[2][32 * NB + 8];
+  alignas(16) float raw[PROD_GROUPS][32 * NB + 8];
   alignas(16) float h[RING * HS];
   alignas(16) float x[RING * XS];
-  alignas(8) unsigned long long full[SLOTS], empty[SLOTS], rawbar[2];
+  alignas(8) unsigned long long full[SLOTS], empty[SLOTS], rawbar[PROD_GROUPS];
 };
 
 struct Params {
@@ -248,8 +249,7 @@ noise_ring_kernel(Params p) {
       mbar_init(&sm.full[i], 4);
       mbar_init(&sm.empty[i], 4);
     }
-    mbar_init(&sm.rawbar[0], 1);
-    mbar_init(&sm.rawbar[1], 1);
+    for (int i = 0; i < PROD_GROUPS; ++i) mbar_init(&sm.rawbar[i], 1);
   }
   __syncthreads();
 
@@ -267,6 +267,7 @@ noise_ring_kernel(Params p) {
     long long g = g_lo;
     Seg sg;
     int pbase = 0, ct = 0;
+    bool dep_done = false;
     while (next_seg(g, g_hi, p.F, sg)) {
       for (int t = 0; t < sg.nC; ++t, ++ct) {
         if ((ct % NPAIR) != pair) continue;
@@ -307,6 +308,13 @@ noise_ring_kernel(Params p) {
           }
         }
         // ---- store / accumulate the 32 outputs of this lane's frame ----
+        if (!dep_done) {
+          // programmatic dependent launch: this grid may have started while the
+          // harmonic kernel was still draining; its audio must be complete (and
+          // visible) before the first add lands.  No-op for a plain launch.
+          asm volatile("griddepcontrol.wait;" ::: "memory");
+          dep_done = true;
+        }
         if (q_rel < sg.len) {
           float* o = p.audio + (size_t)sg.b * p.N + (size_t)(sg.s0 + q_rel) * FRAME +
                      32 * half;
@@ -342,18 +350,17 @@ noise_ring_kernel(Params p) {
   } else {
     // =============================== PRODUCERS ===============================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
-    // Two groups of four warps; group g builds the production tiles P = g (mod 2)
-    // end to end: magnitudes (TMA) -> exp_sigmoid -> both cosine half-sums ->
-    // windowed taps, then the tile's noise rows.  A group has a whole tile-pair
-    // period for one tile, so its latency chains (TMA, MUFU, LDS) stay off the
-    // consumers' critical path.
-    const int grp = (warp - CONS_WARPS) >> 2;         // 0 / 1
+    // PROD_GROUPS groups of four warps; group g builds the production tiles P = g
+    // (mod PROD_GROUPS) end to end: magnitudes (TMA) -> exp_sigmoid (in place) ->
+    // both cosine half-sums -> windowed taps, then the tile's noise rows.  A group
+    // has PROD_GROUPS tile periods for one tile, so its latency chains (TMA, MUFU,
+    // LDS) stay off the consumers' critical path.
+    const int grp = (warp - CONS_WARPS) >> 2;
     const int iw = (warp - CONS_WARPS) & 3;           // column block / slice
     const int ptid = tid - (CONS_WARPS + 4 * grp) * 32;   // 0..127 within the group
     constexpr int PT = 128;
     const int bar_id = 1 + grp;
     float* s_raw = sm.raw[grp];
-    float* s_m = sm.m[grp];
     void* rawbar = &sm.rawbar[grp];
     const float* mags_end = p.mags + (size_t)p.B * p.F * NB;
     // Raw magnitudes of a production tile -> s_raw (asynchronously; consumed one
@@ -408,39 +415,33 @@ noise_ring_kernel(Params p) {
       }
     };
     It cur = it_begin();
-    if (grp == 1 && cur.ok) it_next(cur);
+    for (int i = 0; i < grp && cur.ok; ++i) it_next(cur);
     int roff = 0;
     if (cur.ok) roff = prefetch(cur.sg, cur.tau);
     int n_mine = 0;                                   // tiles this group has staged
     while (cur.ok) {
       It nxt = cur;
-      it_next(nxt);
-      if (nxt.ok) it_next(nxt);
+      for (int i = 0; i < PROD_GROUPS && nxt.ok; ++i) it_next(nxt);
       const Seg& sg = cur.sg;
       const int P = cur.P, slot = P % SLOTS;
       const int jb = sg.s0 - 2 + 32 * cur.tau;
-      // A. magnitudes -> lane-private rows (exp_sigmoid fused, synths.py:176-177)
+      // A. exp_sigmoid in place on the raw rows (synths.py:176-177); rows of frames
+      //    outside [0, F) hold nothing and are forced to zero taps below
       mbar_wait(rawbar, n_mine & 1);
-      named_bar(bar_id, PT);       // the group is done reading s_m (previous tile)
-      {
-        const int j = jb + lane;
-        const bool ok = (j >= 0 && j < p.F);
-        const int k0 = iw * 17;
-        const float* src = s_raw + roff + lane * NB + k0;
-        float* dst = s_m + lane * MS + k0;
+      const bool row_ok = (jb + lane >= 0) && (jb + lane < p.F);
+      const float* mrow = row_ok ? s_raw + roff + lane * NB : s_raw;
+      if (p.raw && row_ok) {
+        float* src = s_raw + roff + lane * NB + iw * 17;
         float v[17];
 #pragma unroll
-        for (int k = 0; k < 17; ++k) v[k] = (ok && k0 + k < NB) ? src[k] : 0.f;
-        if (p.raw) {
+        for (int k = 0; k < 17; ++k) v[k] = (iw * 17 + k < NB) ? src[k] : 0.f;
 #pragma unroll
-          for (int k = 0; k < 17; ++k) v[k] = exp_sigmoid_f(v[k] + p.bias);
-        }
+        for (int k = 0; k < 17; ++k) v[k] = exp_sigmoid_f(v[k] + p.bias);
 #pragma unroll
         for (int k = 0; k < 17; ++k)
-          if (k0 + k < NB) dst[k] = ok ? v[k] : 0.f;
+          if (iw * 17 + k < NB) src[k] = v[k];
       }
-      named_bar(bar_id, PT);       // s_raw consumed, s_m complete
-      if (nxt.ok) roff = prefetch(nxt.sg, nxt.tau);
+      named_bar(bar_id, PT);       // rows complete
       ++n_mine;
       // wait until the consumers have drained this slot
       if (P >= SLOTS) mbar_wait(&sm.empty[slot], ((P / SLOTS) - 1) & 1);
@@ -452,7 +453,6 @@ noise_ring_kernel(Params p) {
         float e8 = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) aE[c] = aO[c] = make_float2(0.f, 0.f);
-        const float* mrow = s_m + lane * MS;
 #pragma unroll 4
         for (int k = 0; k < NO; ++k) {
           const float me = mrow[2 * k], mo = mrow[2 * k + 1];
@@ -479,6 +479,8 @@ noise_ring_kernel(Params p) {
           aE[3] = nf_ffma2(me, make_float2(e1.z, e1.w), aE[3]);
           if (iw == 3) e8 = fmaf(me, sm.te[NO * QP + Q], e8);
         }
+        named_bar(bar_id, PT);     // the group is done reading the rows
+        if (nxt.ok) roff = prefetch(nxt.sg, nxt.tau);
         float* hr = sm.h + (slot * 32 + lane) * HS + HPAD;
         const float E[8] = {aE[0].x, aE[0].y, aE[1].x, aE[1].y,
                             aE[2].x, aE[2].y, aE[3].x, aE[3].y};
@@ -487,14 +489,15 @@ noise_ring_kernel(Params p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int n = n0 + c;
-          const float hp = E[c] + O[c];                // |offset| = n
-          const float hm = E[c] - O[c];                // |offset| = 64 - n
+          const float hp = row_ok ? E[c] + O[c] : 0.f;   // |offset| = n
+          const float hm = row_ok ? E[c] - O[c] : 0.f;   // |offset| = 64 - n
           hr[SHIFT + n] = sm.win[SHIFT + n] * hp;
           if (n != 0) hr[SHIFT - n] = sm.win[SHIFT - n] * hp;
           if (n != 0) hr[S - n] = sm.win[S - n] * hm;  // tap 64 + (64 - n)
           hr[n] = sm.win[n] * hm;                      // tap 64 - (64 - n)
         }
         if (iw == 3) {                                 // n = 32: O[32] = 0
+          if (!row_ok) e8 = 0.f;
           hr[SHIFT + Q] = sm.win[SHIFT + Q] * e8;
           hr[SHIFT - Q] = sm.win[SHIFT - Q] * e8;
         }
@@ -563,7 +566,7 @@ inline bool noise_ring_supported(int F, int nb, int N, int window_size) {
 inline int launch_noise_ring(const float* mags, const float* noise, uint64_t seed,
                              uint64_t offset, float* audio, int B, int F, int N,
                              int accumulate, cudaStream_t st, int raw, float bias,
-                             int item_base) {
+                             int item_base, int overlap_previous = 0) {
   nr_::Params p;
   p.mags = mags; p.noise = noise; p.audio = audio; p.seed = seed; p.offset = offset;
   p.B = B; p.F = F; p.N = N; p.accumulate = accumulate; p.raw = raw; p.bias = bias;
@@ -581,7 +584,25 @@ inline int launch_noise_ring(const float* mags, const float* noise, uint64_t see
   // one persistent CTA per SM; tiny workloads get one CTA per 32-frame tile
   const int grid = (int)std::max<long long>(
       1, std::min<long long>((long long)kNumSMs, (T + 31) / 32));
-  nr_::noise_ring_kernel<<<grid, nr_::THREADS, smem, st>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(nr_::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  // Programmatic dependent launch (decoder path): let this grid's CTAs start on
+  // SMs the harmonic kernel has already vacated - tables, TMA, the first impulse
+  // responses and noise rows do not depend on it; the consumers wait
+  // (griddepcontrol.wait) before their first add into the audio buffer.
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = overlap_previous ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, nr_::noise_ring_kernel, p);
+  if (e != cudaSuccess) {
+    set_error("filtered_noise_forward(ring): launch failed: %s", cudaGetErrorString(e));
+    return DDSP_B200_E_CUDA;
+  }
   DDSP_CHECK_LAUNCH("filtered_noise_forward(ring)");
   return 0;
 }

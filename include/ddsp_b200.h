@@ -167,10 +167,11 @@ int ddsp_b200_decoder_forward(const float* amps_raw, const float* hd_raw,
 /* The same decoder for HOST buffers - what a caller of the reference's
  * ProcessorGroup.__call__ holds when its network outputs are numpy arrays
  * (processors_test.py:35-42) and it wants numpy audio back.  The batch is cut
- * into n_chunks groups of items; chunk c's host->device copies, its two kernels
- * and its device->host audio copy run on three streams and overlap with the
- * neighbouring chunks', so the call costs about max(H2D, compute, D2H) instead
- * of their sum.  Results are identical to ddsp_b200_decoder_forward on the whole
+ * into at most n_chunks groups of items whose sizes halve (16, 8, 4, 4 of 32:
+ * the tail of the call is the last chunk's compute + copy-out, so it is kept
+ * small); chunk c's host->device copies, its two kernels and its device->host
+ * audio copy run on three streams and overlap with the neighbouring chunks', so
+ * the call costs about max(H2D, compute, D2H) instead of their sum.  Results are identical to ddsp_b200_decoder_forward on the whole
  * batch (the Philox item index of a chunk's rows is offset accordingly).
  *
  * The pipeline handle owns one device staging allocation for max_B items of

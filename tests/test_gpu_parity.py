@@ -340,3 +340,43 @@ def test_oscillator_bank_silent_above_nyquist(sample_rate):
   wav = _np(core.oscillator_bank(ones * freqs.astype(np.float32), ones,
                                  sample_rate=sample_rate))
   assert wav.shape == (2, 16000) and np.all(wav == 0.0)
+
+
+@pytest.mark.parametrize('B,F', [(37, 97), (5, 250), (150, 33)])
+def test_filtered_noise_ring_segments_match_oracle(B, F):
+  """The ring kernel hands each persistent CTA a contiguous run of frames that is
+  cut wherever an item ends: shapes whose runs start and stop at every possible
+  offset (ragged last tiles, runs shorter than a tile, items shorter than the
+  3-frame halo of a run)."""
+  nb, N = 65, F * 64
+  rng = np.random.default_rng(B * 1000 + F)
+  mags = rng.uniform(0.0, 1.0, (B, F, nb)).astype(np.float32)
+  noise = rng.uniform(-1, 1, (B, N)).astype(np.float32)
+  want = oracle.frequency_filter(noise, mags, window_size=0)
+  got = _np(core.filtered_noise(mags, N, window_size=0, noise=noise))
+  emax, el2 = rel_err(got, want)
+  assert emax < TOL and el2 < TOL, (emax, el2)
+  # accumulate mode (the fused Add) on top of a known signal
+  base = rng.standard_normal((B, N)).astype(np.float32)
+  out = torch.from_numpy(base.copy()).cuda()
+  core.filtered_noise(mags, N, window_size=0, noise=noise, out=out, accumulate=True)
+  emax, el2 = rel_err(_np(out) - base, want)
+  assert emax < 2 * TOL and el2 < 2 * TOL, (emax, el2)
+
+
+def test_decoder_is_deterministic_at_full_size():
+  """Same seed and offset -> the same bits, twice, at B=64 x 64000 samples: the
+  producer / consumer hand-offs of the noise kernel and the programmatic
+  dependent launch behind the harmonic kernel leave no run-to-run freedom."""
+  B, F, K, nb, N = 64, 1000, 100, 65, 64000
+  inp = synth_inputs(B, F, K, nb, N, seed=77)
+  dev = {k: torch.from_numpy(inp[k]).cuda() for k in
+         ['amps', 'harmonic_distribution', 'f0_hz', 'noise_magnitudes']}
+  outs = []
+  for _ in range(3):
+    outs.append(core.decoder_forward(dev['amps'], dev['harmonic_distribution'],
+                                     dev['f0_hz'], dev['noise_magnitudes'], N,
+                                     window_size=0, seed=5, offset=9))
+  torch.cuda.synchronize()
+  assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+  assert torch.isfinite(outs[0]).all()

@@ -14,9 +14,9 @@ group = ddsp_b200.ProcessorGroup(dag=[
     (ddsp_b200.Harmonic(), ['amps', 'harmonic_distribution', 'f0_hz']),
     (ddsp_b200.FilteredNoise(window_size=0), ['noise_magnitudes']),
     (ddsp_b200.Add(), ['filtered_noise/signal', 'harmonic/signal'])])
-for chunks in (1, 2, 4, 8, 16, 32):
+for chunks in (1, 2, 3, 4, 5, 6, 8):
   dec = ddsp_b200.HostDecoder(group, B, 1000, 100, 65, n_chunks=chunks)
-  for _ in range(5): dec(pinned, out=out)
+  for _ in range(150): dec(pinned, out=out)
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
   for _ in range(30): dec(pinned, out=out)

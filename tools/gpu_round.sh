@@ -12,6 +12,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   --log-file $O/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${TAG}_bench_under_ncu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv \
   --log-file $O/${TAG}_launches_b256.csv python tools/prof_run.py 256 3 > $O/${TAG}_prof256.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'harmonic_fast|noise_pipe' \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'harmonic_v2|noise_ring' \
   --launch-skip 4 -c 2 -f -o $O/${TAG}_full_b256 python tools/prof_run.py 256 3 > $O/${TAG}_ncu_full.log 2>&1
 tail -3 $O/${TAG}_pytest_gpu.log; cat $O/${TAG}_bench_n1.json; cat $O/${TAG}_bench_reference.json; cat $O/${TAG}_prof256.log | tail -2
