@@ -37,14 +37,25 @@ namespace ddsp {
 namespace nr_ {
 constexpr int NB = 65, FRAME = 64, S = 128, S0 = 128, Q = 32, QP = 36;
 constexpr int NE = 33, NO = 32, SHIFT = 64;
+// A consumer warp owns a UNIT of 2 NW outputs of 32 frames: NW tap pairs in its
+// register window, NW + NW + 1 packed accumulators.  NW = 16 (two units per frame,
+// ~150 registers, 9 KB FIR bodies) and NW = 8 (four units, 96 registers, bodies
+// that fit the 6 KB L0 instruction cache, twice the shared-memory loads per
+// FFMA2) were both measured: 343 vs 357 us per B=256 decoder step.  The FIR is
+// bound by the FMA pipe either way - FFMA2 with a broadcast scalar operand issues
+// every 2.4 cycles per sub-partition, not 2 (tools/microbench2.cu).
+constexpr int NW = 16;
+constexpr int UPT = FRAME / (2 * NW);              // units per 64-sample frame
 constexpr int CONS_WARPS = 8, PROD_GROUPS = 3, PROD_WARPS = 4 * PROD_GROUPS;
-constexpr int SLOTS = CONS_WARPS / 2 + 3;          // 32-row slots in the ring: the
-// consumer pairs hold NPAIR + 1 of them, each producer group fills one more
+constexpr int NTG = CONS_WARPS / UPT;              // consumption tiles in flight
+// 32-row slots in the ring: the consumers hold NTG + 1 of them, each producer
+// group fills one more - as far as 227 KB of shared memory go (7 slots)
+constexpr int SLOTS = (NTG + 1 + PROD_GROUPS) < 7 ? (NTG + 1 + PROD_GROUPS) : 7;
 constexpr int RING = 32 * SLOTS;
 constexpr int THREADS = 32 * (CONS_WARPS + PROD_WARPS);
-// 640 threads launch with 96 registers each; the consumers (256 threads) grow to
-// CONS_REGS out of what the producers (384 threads) give back.
-constexpr int CONS_REGS = 144, PROD_REGS = 64;
+// NW = 16 only: 640 threads launch with 96 registers each; the consumers (256
+// threads) grow to CONS_REGS out of what the producers (384 threads) give back.
+constexpr int CONS_REGS = (NW == 16) ? 144 : 0, PROD_REGS = 64;
 constexpr int HPAD = 2, HS = 134, XS = 66, MS = 65;   // row strides (floats)
 constexpr int NQ = FRAME / 4;
 
@@ -97,23 +108,21 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 // ---- consumer: FIR bodies ---------------------------------------------------
-// Window convention: at step e (inputs 2e, 2e+1) W[(c - e) & 15] = (h[m], h[m+1])
+// Window convention: at step e (inputs 2e, 2e+1) W[(c - e) mod NW] = (h[m], h[m+1])
 // with m = N0 + 2c + C - 2e: the tap pair that takes x[2e] to outputs (N0+2c,
 // N0+2c+1) [set A] and x[2e+1] to (N0+2c+1, N0+2c+2) [set B].  Bm1 is set B's
 // pair c = -1 (outputs N0-1, N0): at step e it takes x[2e-1] with W_e[0].
 struct Acc {
-  float2 A[16], B[16], Bm1;
+  float2 A[NW], B[NW], Bm1;
 };
 
-// The FIR of one output block runs as a short PROGRAM of 16-step bodies, executed
-// by a loop with a switch so that each body exists once in the instruction stream
-// (fully inlined per call site the consumer code was 80 KB and the warps stalled
-// on instruction fetch, ncu "no_instruction" 3.6 - profiles/r01_ncu_ring1.txt).
-// A body walks 16 steps k = 0..15 of one row: inputs xp[2k], xp[2k+1]; the tap
-// pair of (c, k) sits at hp + 2c - 2k.
+// The FIR of one unit runs as a short PROGRAM of NW-step bodies, executed by a
+// loop with a switch so that each body exists once in the instruction stream.
+// A body walks NW steps k of one row: inputs xp[2k], xp[2k+1]; the tap pair of
+// (c, k) sits at hp + 2c - 2k.
 //   FULL : every pair (c, k) matters.
-//   LOWER: only c >= k + 1 (taps left of the row start are zero), 15 steps, no
-//          new pair ever enters the window.
+//   LOWER: only c >= k + 1 (taps left of the row start are zero), NW - 1 steps,
+//          no new pair ever enters the window.
 //   UPPER: only c <= k (taps right of the row end are zero); the window fills up
 //          from pair 0.
 enum { OP_FULL = 0, OP_LOWER = 1, OP_UPPER = 2 };
@@ -121,51 +130,58 @@ struct Op {
   const float* xp;
   const float* hp;
   int kind;
-  int preload;      // 0: window continues, 1: load all 16 pairs, 2: pair 0 only
+  int preload;      // 0: window continues, 1: load all NW pairs, 2: pair 0 only
   int set_xo;       // xo_prev := xo before the body
   float xo;
-  int final_op;     // afterwards: Bm1 += xo_prev * W_16[0]  (the last odd input)
+  int final_op;     // afterwards: Bm1 += xo_prev * W[0]  (the last odd input)
 };
+constexpr int N_OPS = 2 * UPT + 1;
 
-// Op i (0..4) of the block program.  x_m1 / h_m1: rows of frame q+1 (tap offset
-// C = -2); x_0 / h_0: frame q (C = 62); x_p1 / h_p1: frame q-1 (C = 126).  h_*
-// point at tap 0; N0 = 0 or 32.
-__device__ __forceinline__ Op block_op(int i, int N0, const float* x_m1,
+// Op i of unit u (outputs N0 = 2 NW u ..).  x_m1 / h_m1: rows of frame q+1 (tap
+// offset C = -2); x_0 / h_0: frame q (C = 62); x_p1 / h_p1: frame q-1 (C = 126).
+// h_* point at tap 0.  Body j of a row covers inputs 2 NW j .. 2 NW (j+1) - 1.
+//   frame q  : UPT FULL bodies (every (n, i) pair is in range); the closing op
+//              (x[63] with taps (N0-2, N0-1)) is all padding for N0 = 0.
+//   frame q+1: reaches outputs n >= i + 2: u FULL bodies, then the shrinking
+//              triangle.
+//   frame q-1: covers i >= n - 1: the growing triangle in body u (entered with
+//              x[N0-1] -> output N0), then FULL bodies to the end of the row.
+__device__ __forceinline__ Op block_op(int i, int u, const float* x_m1,
                                        const float* h_m1, const float* x_0,
                                        const float* h_0, const float* x_p1,
                                        const float* h_p1) {
-  // frame q: all 64 inputs, every pair valid.  The closing op (x[63] with taps
-  // (N0 - 2, N0 - 1)) is all padding for N0 = 0.
-  if (i == 0) return Op{x_0, h_0 + N0 + 62, OP_FULL, 1, 1, 0.f, 0};
-  if (i == 1) return Op{x_0 + 32, h_0 + N0 + 30, OP_FULL, 0, 0, 0.f, N0 != 0};
-  if (N0 == 0) {
-    // frame q+1 reaches outputs n >= i + 2 only (steps 0..14); frame q-1 covers
-    // i >= n - 1: a growing triangle over steps 0..15, then everything
-    if (i == 2) return Op{x_m1, h_m1 - 2, OP_LOWER, 1, 0, 0.f, 0};
-    if (i == 3) return Op{x_p1, h_p1 + 126, OP_UPPER, 2, 1, 0.f, 0};
-    return Op{x_p1 + 32, h_p1 + 94, OP_FULL, 0, 0, 0.f, 1};
-  }
-  // frame q+1: steps 0..15 everything, 16..30 the shrinking triangle; frame q-1:
-  // steps 16..31 the growing triangle, entered with x[31] -> output 32
-  if (i == 2) return Op{x_m1, h_m1 + 30, OP_FULL, 1, 1, 0.f, 0};
-  if (i == 3) return Op{x_m1 + 32, h_m1 - 2, OP_LOWER, 0, 0, 0.f, 0};
-  return Op{x_p1 + 32, h_p1 + 126, OP_UPPER, 2, 1, x_p1[31], 1};
+  const int N0 = 2 * NW * u;
+  if (i < UPT)
+    return Op{x_0 + 2 * NW * i, h_0 + N0 + 62 - 2 * NW * i, OP_FULL, i == 0, i == 0,
+              0.f, (i == UPT - 1) && (N0 != 0)};
+  i -= UPT;
+  if (i < u)
+    return Op{x_m1 + 2 * NW * i, h_m1 + N0 - 2 - 2 * NW * i, OP_FULL, i == 0, i == 0,
+              0.f, 0};
+  if (i == u) return Op{x_m1 + N0, h_m1 - 2, OP_LOWER, u == 0, u == 0, 0.f, 0};
+  i -= 1;                                              // body index in frame q-1
+  if (i == u)
+    return Op{x_p1 + N0, h_p1 + 126, OP_UPPER, 2, 1, (u > 0) ? x_p1[N0 - 1] : 0.f,
+              u == UPT - 1};
+  return Op{x_p1 + 2 * NW * i, h_p1 + N0 + 126 - 2 * NW * i, OP_FULL, 0, 0, 0.f,
+            i == UPT - 1};
 }
 
-__device__ __forceinline__ void consume_block(Acc& a, int N0, const float* x_m1,
+__device__ __forceinline__ void consume_block(Acc& a, int u, const float* x_m1,
                                               const float* h_m1, const float* x_0,
                                               const float* h_0, const float* x_p1,
                                               const float* h_p1) {
-  float2 W[16];
+  float2 W[NW];
   float xo_prev = 0.f;
+  constexpr int M = NW - 1;
 #pragma unroll 1
-  for (int i = 0; i < 5; ++i) {
-    const Op op = block_op(i, N0, x_m1, h_m1, x_0, h_0, x_p1, h_p1);
+  for (int i = 0; i < N_OPS; ++i) {
+    const Op op = block_op(i, u, x_m1, h_m1, x_0, h_0, x_p1, h_p1);
     const float* __restrict__ xp = op.xp;
     const float* __restrict__ hp = op.hp;
     if (op.preload == 1) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) W[c] = *reinterpret_cast<const float2*>(hp + 2 * c);
+      for (int c = 0; c < NW; ++c) W[c] = *reinterpret_cast<const float2*>(hp + 2 * c);
     } else if (op.preload == 2) {
       W[0] = *reinterpret_cast<const float2*>(hp);
     }
@@ -173,46 +189,46 @@ __device__ __forceinline__ void consume_block(Acc& a, int N0, const float* x_m1,
     switch (op.kind) {
       case OP_FULL:
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < NW; ++k) {
           const float2 xv = *reinterpret_cast<const float2*>(xp + 2 * k);
-          // pair 15 first: its slot is refilled (for step k + 1) right behind it
-          a.A[15] = nf_ffma2(xv.x, W[(15 - k) & 15], a.A[15]);
-          a.B[15] = nf_ffma2(xv.y, W[(15 - k) & 15], a.B[15]);
+          // last pair first: its slot is refilled (for step k + 1) right behind it
+          a.A[M] = nf_ffma2(xv.x, W[(M - k) & M], a.A[M]);
+          a.B[M] = nf_ffma2(xv.y, W[(M - k) & M], a.B[M]);
           const float2 wn = *reinterpret_cast<const float2*>(hp - 2 * (k + 1));
 #pragma unroll
-          for (int c = 14; c >= 0; --c) {
-            a.A[c] = nf_ffma2(xv.x, W[(c - k) & 15], a.A[c]);
-            a.B[c] = nf_ffma2(xv.y, W[(c - k) & 15], a.B[c]);
+          for (int c = M - 1; c >= 0; --c) {
+            a.A[c] = nf_ffma2(xv.x, W[(c - k) & M], a.A[c]);
+            a.B[c] = nf_ffma2(xv.y, W[(c - k) & M], a.B[c]);
           }
-          a.Bm1 = nf_ffma2(xo_prev, W[(0 - k) & 15], a.Bm1);
-          W[(15 - k) & 15] = wn;
+          a.Bm1 = nf_ffma2(xo_prev, W[(0 - k) & M], a.Bm1);
+          W[(M - k) & M] = wn;
           xo_prev = xv.y;
         }
         break;
       case OP_LOWER:
 #pragma unroll
-        for (int k = 0; k < 15; ++k) {
+        for (int k = 0; k < NW - 1; ++k) {
           const float2 xv = *reinterpret_cast<const float2*>(xp + 2 * k);
 #pragma unroll
-          for (int c = 15; c >= k + 1; --c) {
-            a.A[c] = nf_ffma2(xv.x, W[(c - k) & 15], a.A[c]);
-            a.B[c] = nf_ffma2(xv.y, W[(c - k) & 15], a.B[c]);
+          for (int c = M; c >= k + 1; --c) {
+            a.A[c] = nf_ffma2(xv.x, W[(c - k) & M], a.A[c]);
+            a.B[c] = nf_ffma2(xv.y, W[(c - k) & M], a.B[c]);
           }
           xo_prev = xv.y;
         }
         break;
       default:
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < NW; ++k) {
           const float2 xv = *reinterpret_cast<const float2*>(xp + 2 * k);
           const float2 wn = *reinterpret_cast<const float2*>(hp - 2 * (k + 1));
 #pragma unroll
           for (int c = k; c >= 0; --c) {
-            a.A[c] = nf_ffma2(xv.x, W[(c - k) & 15], a.A[c]);
-            a.B[c] = nf_ffma2(xv.y, W[(c - k) & 15], a.B[c]);
+            a.A[c] = nf_ffma2(xv.x, W[(c - k) & M], a.A[c]);
+            a.B[c] = nf_ffma2(xv.y, W[(c - k) & M], a.B[c]);
           }
-          a.Bm1 = nf_ffma2(xo_prev, W[(0 - k) & 15], a.Bm1);
-          W[(15 - k) & 15] = wn;
+          a.Bm1 = nf_ffma2(xo_prev, W[(0 - k) & M], a.Bm1);
+          W[(M - k) & M] = wn;
           xo_prev = xv.y;
         }
         break;
@@ -247,7 +263,7 @@ noise_ring_kernel(Params p) {
   if (tid == 0) {
     for (int i = 0; i < SLOTS; ++i) {
       mbar_init(&sm.full[i], 4);
-      mbar_init(&sm.empty[i], 4);
+      mbar_init(&sm.empty[i], 2 * UPT);
     }
     for (int i = 0; i < PROD_GROUPS; ++i) mbar_init(&sm.rawbar[i], 1);
   }
@@ -260,17 +276,16 @@ noise_ring_kernel(Params p) {
 
   if (warp < CONS_WARPS) {
     // =========================== CONSUMERS ===================================
-    // (two warpgroups; the FIR wants ~150 registers: take them from the producers)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
-    const int pair = warp >> 1, half = warp & 1;
-    constexpr int NPAIR = CONS_WARPS / 2;
+    if (CONS_REGS != 0)   // NW = 16: the FIR wants ~150 registers, from the producers
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS ? CONS_REGS : 96));
+    const int tg = warp / UPT, unit = warp % UPT;      // tile group, unit of the tile
     long long g = g_lo;
     Seg sg;
     int pbase = 0, ct = 0;
     bool dep_done = false;
     while (next_seg(g, g_hi, p.F, sg)) {
       for (int t = 0; t < sg.nC; ++t, ++ct) {
-        if ((ct % NPAIR) != pair) continue;
+        if ((ct % NTG) != tg) continue;
         // rows of this tile live in production tiles t and t+1 of the segment
         // (two producer groups finish tiles out of order: wait for both)
         {
@@ -287,17 +302,17 @@ noise_ring_kernel(Params p) {
         auto hrow = [&](int r) { return sm.h + ((rbase + r) % RING) * HS + HPAD; };
         Acc a;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) a.A[c] = a.B[c] = make_float2(0.f, 0.f);
+        for (int c = 0; c < NW; ++c) a.A[c] = a.B[c] = make_float2(0.f, 0.f);
         a.Bm1 = make_float2(0.f, 0.f);
-        consume_block(a, 32 * half, xrow(rho + 1), hrow(rho + 1), xrow(rho), hrow(rho),
+        consume_block(a, unit, xrow(rho + 1), hrow(rho + 1), xrow(rho), hrow(rho),
                       xrow(rho - 1), hrow(rho - 1));
         // frame q-2 reaches output 0 only: input 63 through tap 127
-        if (half == 0)
+        if (unit == 0)
           a.A[0].x = fmaf(xrow(rho - 2)[63], hrow(rho - 2)[127], a.A[0].x);
         __syncwarp();
         if (lane == 0) {
           // release the slots: a production tile is read by consumption tiles
-          // tau-1 and tau (two warps each); a lone reader arrives twice.
+          // tau-1 and tau (UPT warps each); a lone reader arrives twice.
 #pragma unroll
           for (int d = 0; d < 2; ++d) {
             const int tau = t + d;
@@ -307,7 +322,7 @@ noise_ring_kernel(Params p) {
             }
           }
         }
-        // ---- store / accumulate the 32 outputs of this lane's frame ----
+        // ---- store / accumulate this lane's 2 NW outputs ----
         if (!dep_done) {
           // programmatic dependent launch: this grid may have started while the
           // harmonic kernel was still draining; its audio must be complete (and
@@ -316,30 +331,31 @@ noise_ring_kernel(Params p) {
           dep_done = true;
         }
         if (q_rel < sg.len) {
-          float* o = p.audio + (size_t)sg.b * p.N + (size_t)(sg.s0 + q_rel) * FRAME +
-                     32 * half;
-          float v[32];
+          constexpr int NOUT = 2 * NW;
+          const long long t0 = (long long)(sg.s0 + q_rel) * FRAME + NOUT * unit;
+          float* o = p.audio + (size_t)sg.b * p.N + t0;
+          float v[NOUT];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
+          for (int c = 0; c < NW; ++c) {
             const float2 bp = (c == 0) ? a.Bm1 : a.B[c - 1];
             v[2 * c] = a.A[c].x + bp.y;
             v[2 * c + 1] = a.A[c].y + a.B[c].x;
           }
-          const long long t0 = (long long)(sg.s0 + q_rel) * FRAME + 32 * half;
-          if (t0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+          if (t0 + NOUT <= p.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int w4 = 0; w4 < NOUT / 4; ++w4) {
               if (p.accumulate)
-                red_add_v4(o + 4 * u, v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                red_add_v4(o + 4 * w4, v[4 * w4], v[4 * w4 + 1], v[4 * w4 + 2],
+                           v[4 * w4 + 3]);
               else
-                *reinterpret_cast<float4*>(o + 4 * u) =
-                    make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                *reinterpret_cast<float4*>(o + 4 * w4) =
+                    make_float4(v[4 * w4], v[4 * w4 + 1], v[4 * w4 + 2], v[4 * w4 + 3]);
             }
           } else {
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-              if (t0 + u < p.N) {
-                if (p.accumulate) o[u] += v[u]; else o[u] = v[u];
+            for (int w1 = 0; w1 < NOUT; ++w1) {
+              if (t0 + w1 < p.N) {
+                if (p.accumulate) o[w1] += v[w1]; else o[w1] = v[w1];
               }
             }
           }
@@ -349,7 +365,8 @@ noise_ring_kernel(Params p) {
     }
   } else {
     // =============================== PRODUCERS ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
+    if (CONS_REGS != 0)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
     // PROD_GROUPS groups of four warps; group g builds the production tiles P = g
     // (mod PROD_GROUPS) end to end: magnitudes (TMA) -> exp_sigmoid (in place) ->
     // both cosine half-sums -> windowed taps, then the tile's noise rows.  A group
