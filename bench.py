@@ -343,10 +343,28 @@ def run_ours(args):
     harm.get_controls(d['amps'], d['harmonic_distribution'], d['f0_hz'])
     noise.get_controls(d['noise_magnitudes'])
 
-  k_steps = max(args.steps, 20)
-  ms_harm = timed(harm_only, k_steps, 5) / k_steps
-  ms_noise = timed(noise_only, k_steps, 5) / k_steps
-  ms_ctl = timed(controls_only, k_steps, 5) / k_steps
+  def kernel_ms(fn, steps=40, warmup=5):
+    """Mean GPU duration of ONE call: an event pair around every launch (in-stream
+    events serialise with the kernels, so a pair brackets exactly its own launch
+    whether or not the host keeps the queue full - these single kernels are
+    shorter than the Python that launches them)."""
+    for i in range(warmup):
+      fn(i)
+    torch.cuda.synchronize()
+    pairs = []
+    for i in range(steps):
+      e0 = torch.cuda.Event(enable_timing=True)
+      e1 = torch.cuda.Event(enable_timing=True)
+      e0.record()
+      fn(warmup + i)
+      e1.record()
+      pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in pairs) / steps
+
+  ms_harm = kernel_ms(harm_only)
+  ms_noise = kernel_ms(noise_only)
+  ms_ctl = kernel_ms(controls_only)
   clocks = sampler.stop() if rank == 0 else None
 
   # -- secondary workload: C3 (B=256) for context ------------------------------

@@ -253,8 +253,11 @@ __device__ __forceinline__ void controls_rows(float* __restrict__ sXw,
   }
 }
 
+#ifndef DDSP_HV2_MIN_CTAS
+#define DDSP_HV2_MIN_CTAS 4
+#endif
 template <bool WINDOW, int HOPT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, DDSP_HV2_MIN_CTAS)
 harmonic_v2_kernel(HarmonicParams p, int use_tma, int FW) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int hop = HOPT ? HOPT : p.hop;
@@ -452,9 +455,9 @@ inline int launch_harmonic_v2(HarmonicParams p, cudaStream_t st) {
   // Frames per warp: 8 amortises the per-warp prologue best; fewer when the grid
   // would not fill the chip a few times over (the CTAs' work varies ~10x with f0,
   // so several waves are needed for the block scheduler to balance it).
-  // (measured, B200: B=256 -> FW 8/16 equal, FW 4 +12 %; B=32 -> FW 4 best, FW 2
-  // and FW 8 +14 % / +9 %)
-  int FW = 8;
+  // (measured, B200, HBM-cold inputs: B=256 -> FW 16 / 8 / 4 / 2 = 163 / 163 / 183 /
+  // 238 us; B=32 -> 37.8 / 34.9 / 31.1 / 35.0 us)
+  int FW = 16;
   const long long want_ctas = 8ll * kNumSMs;
   while (FW > 4 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < want_ctas) FW >>= 1;
   while (FW > 1 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < kNumSMs) FW >>= 1;
