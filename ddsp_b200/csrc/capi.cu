@@ -17,6 +17,7 @@
 #include "host_pipeline.cuh"
 #include "backward.cuh"
 #include "oscbank.cuh"
+#include "spectral.cuh"
 
 namespace ddsp {
 
@@ -775,6 +776,64 @@ int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,
   if (n == 0) return 0;
   add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
   DDSP_CHECK_LAUNCH("add");
+  return 0;
+}
+
+
+// ---- spectrogram-loss pieces -------------------------------------------------
+int ddsp_b200_frame_window(const float* audio, const float* window, float* frames,
+                           int B, int N, int n_frames, int frame_size, int frame_step,
+                           void* stream) {
+  DDSP_REQUIRE(audio && window && frames, DDSP_B200_E_INVALID, "frame_window: null pointer");
+  DDSP_REQUIRE(B >= 0 && N >= 1 && n_frames >= 1 && frame_size >= 4 && frame_size % 4 == 0 &&
+                   frame_step >= 1 && B <= 65535,
+               DDSP_B200_E_INVALID, "frame_window: bad shape B=%d N=%d T=%d n=%d step=%d", B,
+               N, n_frames, frame_size, frame_step);
+  DDSP_REQUIRE((((uintptr_t)window | (uintptr_t)frames) & 15) == 0, DDSP_B200_E_INVALID,
+               "frame_window: window / frames must be 16-byte aligned");
+  if (B == 0) return 0;
+  const long long quads = ((long long)n_frames * frame_size) / 4;
+  dim3 grid((unsigned)((quads + 255) / 256), B);
+  frame_window_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(audio, window, frames, N, n_frames,
+                                                            frame_size, frame_step);
+  DDSP_CHECK_LAUNCH("frame_window");
+  return 0;
+}
+
+int ddsp_b200_frame_window_adjoint(const float* grad_frames, const float* window,
+                                   float* grad_audio, int B, int N, int n_frames,
+                                   int frame_size, int frame_step, void* stream) {
+  DDSP_REQUIRE(grad_frames && window && grad_audio, DDSP_B200_E_INVALID,
+               "frame_window_adjoint: null pointer");
+  DDSP_REQUIRE(B >= 0 && N >= 1 && n_frames >= 1 && frame_size >= 1 && frame_step >= 1 &&
+                   B <= 65535,
+               DDSP_B200_E_INVALID, "frame_window_adjoint: bad shape");
+  if (B == 0) return 0;
+  dim3 grid((N + 255) / 256, B);
+  frame_window_adjoint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      grad_frames, window, grad_audio, N, n_frames, frame_size, frame_step);
+  DDSP_CHECK_LAUNCH("frame_window_adjoint");
+  return 0;
+}
+
+int ddsp_b200_spectral_l1(const float* stft_target, const float* stft_value,
+                          float* grad_value, double* sums, int64_t n_bins_total,
+                          float mag_weight, float logmag_weight, int n_bins,
+                          int irfft_size, void* stream) {
+  DDSP_REQUIRE(stft_target && stft_value && grad_value && sums, DDSP_B200_E_INVALID,
+               "spectral_l1: null pointer");
+  DDSP_REQUIRE(n_bins_total >= 1 && n_bins >= 1 && n_bins_total % n_bins == 0 &&
+                   (irfft_size == 0 || irfft_size == 2 * (n_bins - 1)),
+               DDSP_B200_E_INVALID, "spectral_l1: bad sizes (total %lld, bins %d, irfft %d)",
+               (long long)n_bins_total, n_bins, irfft_size);
+  DDSP_REQUIRE((((uintptr_t)stft_target | (uintptr_t)stft_value | (uintptr_t)grad_value) & 15) == 0,
+               DDSP_B200_E_INVALID, "spectral_l1: tensors must be 16-byte aligned");
+  const long long blocks = std::min<long long>((n_bins_total / 2 + 255) / 256 + 1, 8ll * kNumSMs);
+  spectral_l1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(stft_target), reinterpret_cast<const float2*>(stft_value),
+      reinterpret_cast<float2*>(grad_value), sums, n_bins_total, mag_weight, logmag_weight,
+      1.0f / (float)n_bins_total, 1e-5f, n_bins, irfft_size);
+  DDSP_CHECK_LAUNCH("spectral_l1");
   return 0;
 }
 

@@ -61,7 +61,35 @@ class SpectralLoss:
     """losses.Loss.get_losses_dict (losses.py:60-66)."""
     return {self.name: self.call(target_audio, audio, **kwargs)}
 
+  def _fusable(self, target_audio, audio, weights):
+    """The ae.gin configuration (L1 on magnitudes and log-magnitudes,
+    ae.gin:39-41) on CUDA tensors runs through three hand-written kernels per FFT
+    size around cuFFT instead of ~70 elementwise launches."""
+    return (torch.is_tensor(audio) and audio.is_cuda and torch.is_tensor(target_audio)
+            and target_audio.is_cuda and weights is None
+            and self.loss_type.upper() == 'L1'
+            and self.delta_time_weight <= 0 and self.delta_freq_weight <= 0
+            and self.cumsum_freq_weight <= 0
+            and (self.mag_weight > 0 or self.logmag_weight > 0)
+            and audio.dim() == 2 and target_audio.shape == audio.shape
+            and all(int(sz) >= 16 and (int(sz) & (int(sz) - 1)) == 0
+                    for sz in self.fft_sizes))
+
+  def _call_fused(self, target_audio, audio):
+    loss = 0.0
+    with torch.no_grad():
+      target = target_audio.to(torch.float32)
+    for size in self.fft_sizes:
+      with torch.no_grad():
+        stft_t = spectral_ops.stft_cuda(target, size)
+      loss = loss + spectral_ops.SpectralTermFn.apply(
+          stft_t, audio, int(size), int(size * 0.25), max(self.mag_weight, 0.0),
+          max(self.logmag_weight, 0.0))
+    return loss
+
   def call(self, target_audio, audio, weights=None):
+    if self._fusable(target_audio, audio, weights):
+      return self._call_fused(target_audio, audio)
     loss = 0.0
     diff = lambda x, axis: torch.diff(x, dim=axis)
     for loss_op in self.spectrogram_ops:

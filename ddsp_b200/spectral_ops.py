@@ -40,3 +40,117 @@ def stft(audio, frame_size=2048, overlap=0.75, pad_end=True):
 def compute_mag(audio, size=2048, overlap=0.75, pad_end=True):
   """spectral_ops.compute_mag (spectral_ops.py:67-70)."""
   return torch.abs(stft(audio, frame_size=size, overlap=overlap, pad_end=pad_end))
+
+
+# ---- CUDA pieces of the spectrogram loss (include/ddsp_b200.h) ---------------
+_WINDOWS = {}
+
+
+def _hann(frame_size, device):
+  key = (int(frame_size), str(device))
+  if key not in _WINDOWS:
+    _WINDOWS[key] = torch.hann_window(int(frame_size), periodic=True,
+                                      dtype=torch.float32, device=device)
+  return _WINDOWS[key]
+
+
+def _stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+class FrameWindowFn(torch.autograd.Function):
+  """stft's framing + periodic Hann window (pad_end=True) as one CUDA kernel,
+  and its transpose (windowed overlap-add of the frame gradients) for backward.
+  audio [B, N] -> frames [B, ceil(N / step), frame_size]."""
+
+  @staticmethod
+  def forward(ctx, audio, frame_size, step):
+    from ddsp_b200 import _lib
+    audio = audio.contiguous()
+    b, n = audio.shape
+    n_frames = -(-n // step)
+    frames = torch.empty((b, n_frames, frame_size), dtype=torch.float32,
+                         device=audio.device)
+    _lib.check(_lib.load().ddsp_b200_frame_window(
+        audio.data_ptr(), _hann(frame_size, audio.device).data_ptr(),
+        frames.data_ptr(), b, n, n_frames, frame_size, step, _stream()))
+    ctx.meta = (b, n, n_frames, frame_size, step)
+    return frames
+
+  @staticmethod
+  def backward(ctx, grad_frames):
+    from ddsp_b200 import _lib
+    b, n, n_frames, frame_size, step = ctx.meta
+    grad_frames = grad_frames.contiguous()
+    grad_audio = torch.empty((b, n), dtype=torch.float32, device=grad_frames.device)
+    _lib.check(_lib.load().ddsp_b200_frame_window_adjoint(
+        grad_frames.data_ptr(), _hann(frame_size, grad_frames.device).data_ptr(),
+        grad_audio.data_ptr(), b, n, n_frames, frame_size, step, _stream()))
+    return grad_audio, None, None
+
+
+def _frame_window(audio, frame_size, step):
+  from ddsp_b200 import _lib
+  audio = audio.contiguous()
+  b, n = audio.shape
+  n_frames = -(-n // step)
+  frames = torch.empty((b, n_frames, frame_size), dtype=torch.float32,
+                       device=audio.device)
+  _lib.check(_lib.load().ddsp_b200_frame_window(
+      audio.data_ptr(), _hann(frame_size, audio.device).data_ptr(),
+      frames.data_ptr(), b, n, n_frames, frame_size, step, _stream()))
+  return frames
+
+
+class SpectralTermFn(torch.autograd.Function):
+  """One FFT size of the 'L1' spectrogram loss (losses.py:102-127, 190-243):
+  mag_weight * mean|mag_t - mag_v| + logmag_weight * mean|safe_log mag_t -
+  safe_log mag_v| of audio [B, N] against the target's complex STFT.
+
+  forward : framing + Hann (one kernel), cuFFT r2c, ONE pass over both STFTs that
+            also leaves the gradient w.r.t. the value STFT, pre-scaled so that the
+            transpose of rfft is a plain irfft.
+  backward: cuFFT c2r, windowed overlap-add of the frame gradients (one kernel)."""
+
+  @staticmethod
+  def forward(ctx, stft_target, audio, frame_size, step, mag_weight, logmag_weight):
+    from ddsp_b200 import _lib
+    audio = audio.to(torch.float32).contiguous()
+    frames = _frame_window(audio, frame_size, step)
+    xv = torch.fft.rfft(frames, n=frame_size, dim=-1)
+    del frames
+    xt = stft_target.contiguous()
+    if xt.shape != xv.shape:
+      raise ValueError(f'target STFT {tuple(xt.shape)} vs value STFT {tuple(xv.shape)}')
+    grad = torch.empty_like(xv)
+    sums = torch.zeros(2, dtype=torch.float64, device=xv.device)
+    m = xv.numel()
+    _lib.check(_lib.load().ddsp_b200_spectral_l1(
+        xt.data_ptr(), xv.data_ptr(), grad.data_ptr(), sums.data_ptr(), m,
+        float(mag_weight), float(logmag_weight), xv.shape[-1], frame_size,
+        _stream()))
+    ctx.save_for_backward(grad)
+    ctx.meta = (audio.shape[0], audio.shape[1], xv.shape[1], frame_size, step)
+    w = torch.tensor([mag_weight / m, logmag_weight / m], dtype=torch.float64,
+                     device=xv.device)
+    return (sums * w).sum().to(torch.float32)
+
+  @staticmethod
+  def backward(ctx, grad_out):
+    from ddsp_b200 import _lib
+    (grad,) = ctx.saved_tensors
+    b, n, n_frames, frame_size, step = ctx.meta
+    grad_frames = torch.fft.irfft(grad, n=frame_size, dim=-1).contiguous()
+    grad_audio = torch.empty((b, n), dtype=torch.float32, device=grad.device)
+    _lib.check(_lib.load().ddsp_b200_frame_window_adjoint(
+        grad_frames.data_ptr(), _hann(frame_size, grad.device).data_ptr(),
+        grad_audio.data_ptr(), b, n, n_frames, frame_size, step, _stream()))
+    return None, grad_audio * grad_out, None, None, None, None
+
+
+def stft_cuda(audio, frame_size, overlap=0.75):
+  """stft(pad_end=True) for CUDA tensors through FrameWindowFn + cuFFT."""
+  step = int(frame_size * (1.0 - overlap))
+  fft_length = 1 << (int(frame_size) - 1).bit_length()
+  frames = FrameWindowFn.apply(audio.to(torch.float32), int(frame_size), step)
+  return torch.fft.rfft(frames, n=fft_length, dim=-1)

@@ -231,6 +231,30 @@ int ddsp_b200_oscillator_bank(const float* frequency_envelopes,
 int ddsp_b200_resample(const float* in, float* out, int B, int F, int C, int N,
                        int method, int add_endpoint, void* stream);
 
+/* Pieces of losses.SpectralLoss (losses.py:130-243) around cuFFT.
+ * frame_window: tf.signal.stft's framing + periodic Hann window with pad_end=True
+ * (spectral_ops.py:34-47): audio [B,N] -> frames [B, n_frames, frame_size],
+ * frames[b,t,i] = window[i] * audio[b, t*frame_step + i] (0 past the end).
+ * frame_window_adjoint: its transpose, grad_frames -> grad_audio [B,N].
+ * spectral_l1: for complex STFTs [n_bins_total] (interleaved re/im) of target and
+ * value: sums[0] += sum |mag_t - mag_v|, sums[1] += sum |safe_log mag_t -
+ * safe_log mag_v| (core.py:213-216), and grad_value = d/dX_v of
+ * mag_weight * mean|.| + logmag_weight * mean|.| (losses.py:102-127, 'L1').
+ * n_bins = bins per frame.  irfft_size = 0: grad_value is the plain gradient;
+ * irfft_size = 2 (n_bins - 1): it is pre-scaled so that irfft(grad_value,
+ * irfft_size) is the gradient w.r.t. the real frames (the transpose of rfft).
+ * sums must be zeroed by the caller. */
+int ddsp_b200_frame_window(const float* audio, const float* window, float* frames,
+                           int B, int N, int n_frames, int frame_size, int frame_step,
+                           void* stream);
+int ddsp_b200_frame_window_adjoint(const float* grad_frames, const float* window,
+                                   float* grad_audio, int B, int N, int n_frames,
+                                   int frame_size, int frame_step, void* stream);
+int ddsp_b200_spectral_l1(const float* stft_target, const float* stft_value,
+                          float* grad_value, double* sums, int64_t n_bins_total,
+                          float mag_weight, float logmag_weight, int n_bins,
+                          int irfft_size, void* stream);
+
 /* processors.Add.get_signal (processors.py:174-176). out may alias a or b. */
 int ddsp_b200_add(const float* a, const float* b, float* out, int64_t n,
                   void* stream);
