@@ -415,6 +415,13 @@ def run_ours(args):
     return None
 
   peak, peak_src = _measured_peaks()
+  # DRAM traffic of the same kernels from one ncu --set full capture of this
+  # workload (profiles/r01_traffic_b32.json; null for any other batch size)
+  traffic = {}
+  tpath = os.path.join(ROOT, 'profiles', 'r01_traffic_b32.json')
+  if os.path.exists(tpath):
+    with open(tpath) as f:
+      traffic = {k: v for k, v in json.load(f).items() if v.get('batch') == B}
   dom_is_harm = ms_harm >= ms_noise
   dom_ms = ms_harm if dom_is_harm else ms_noise
   dom_bytes = (BYTES_HARMONIC if dom_is_harm else BYTES_NOISE + 4 * N_SAMPLES) * B
@@ -424,7 +431,10 @@ def run_ours(args):
                'filtered_noise_forward(accumulate)',
       'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
       'frac': achieved / peak, 'peak_source': peak_src + ' (MEASURED_PEAKS.json hbm_gbs)',
-      'traffic': None,
+      'traffic': (traffic.get('harmonic_forward' if dom_is_harm else
+                              'filtered_noise_forward') or {}).get('traffic'),
+      'traffic_source': (traffic.get('harmonic_forward' if dom_is_harm else
+                                     'filtered_noise_forward') or {}).get('source'),
       'algorithmic_bytes_per_launch': dom_bytes,
       'kernel_ms': {'harmonic_forward': ms_harm,
                     'filtered_noise_forward': ms_noise,
@@ -457,7 +467,8 @@ def run_ours(args):
           'noise': 'in-kernel Philox4x32-10', 'parallelism': 'batch-sharded replicas, no collective',
       },
       'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e,
-              'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
+              'h2d_bytes_per_step': h2d_bytes * world,
+              'd2h_bytes_per_step': d2h_bytes * world,
               'api': 'ddsp_b200.HostDecoder(group)(pinned host inputs) -> pinned '
                      'host audio, %d chunks on 3 streams' % best_c,
               'ms_per_step_unpipelined': ms_e2e_serial},
