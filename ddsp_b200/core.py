@@ -118,6 +118,116 @@ def exp_sigmoid(x, exponent=10.0, max_value=2.0, threshold=1e-7):
 
 
 # ----------------------------------------------------------------------------
+# Frequency scaling of network outputs (core.py:207-348, 414-508) - frame-rate
+# torch ops (a few thousand elements per item), device-agnostic.
+# ----------------------------------------------------------------------------
+def _as_f32(x):
+  return x.to(torch.float32) if torch.is_tensor(x) else torch.tensor(
+      x, dtype=torch.float32)
+
+
+def safe_log(x, eps=1e-5):
+  """core.safe_log (core.py:213-216)."""
+  x = _as_f32(x)
+  return torch.log(torch.where(x <= 0.0, torch.full_like(x, eps), x))
+
+
+def logb(x, base=2.0, eps=1e-5):
+  """core.logb (core.py:219-221): safe_divide(safe_log(x), safe_log(base))."""
+  den = safe_log(base, eps)
+  den = torch.where(den == 0.0, torch.full_like(den, eps), den)
+  return safe_log(x, eps) / den
+
+
+def midi_to_hz(notes, midi_zero_silence: bool = False):
+  """core.midi_to_hz (core.py:280-297)."""
+  notes = _as_f32(notes)
+  hz = 440.0 * (2.0 ** ((notes - 69.0) / 12.0))
+  if midi_zero_silence:
+    hz = torch.where(notes == 0.0, torch.zeros_like(hz), hz)
+  return hz
+
+
+def hz_to_midi(frequencies):
+  """core.hz_to_midi (core.py:300-306): 0 Hz maps to MIDI 0."""
+  frequencies = _as_f32(frequencies)
+  notes = 12.0 * (logb(frequencies, 2.0) - logb(440.0, 2.0)) + 69.0
+  return torch.where(frequencies <= 0.0, torch.zeros_like(notes), notes)
+
+
+def unit_to_midi(unit, midi_min=20.0, midi_max=90.0, clip: bool = False):
+  """core.unit_to_midi (core.py:309-315)."""
+  unit = torch.clamp(unit, 0.0, 1.0) if clip else unit
+  return midi_min + (midi_max - midi_min) * unit
+
+
+def midi_to_unit(midi, midi_min=20.0, midi_max=90.0, clip: bool = False):
+  """core.midi_to_unit (core.py:318-324)."""
+  unit = (midi - midi_min) / (midi_max - midi_min)
+  return torch.clamp(unit, 0.0, 1.0) if clip else unit
+
+
+def unit_to_hz(unit, hz_min, hz_max, clip: bool = False):
+  """core.unit_to_hz (core.py:327-336): logarithmic map of [0, 1]."""
+  midi = unit_to_midi(unit, midi_min=hz_to_midi(hz_min), midi_max=hz_to_midi(hz_max),
+                      clip=clip)
+  return midi_to_hz(midi)
+
+
+def hz_to_unit(hz, hz_min, hz_max, clip: bool = False):
+  """core.hz_to_unit (core.py:339-348)."""
+  return midi_to_unit(hz_to_midi(hz), midi_min=hz_to_midi(hz_min),
+                      midi_max=hz_to_midi(hz_max), clip=clip)
+
+
+def _add_depth_axis(freqs, depth: int = 1):
+  """core._add_depth_axis (core.py:414-420): [B, T, N*D] -> [B, T, N, D]."""
+  b, t, combined = freqs.shape
+  return freqs.reshape(b, t, int(combined) // depth, depth)
+
+
+def frequencies_softmax(freqs, depth: int = 1, hz_min: float = 20.0,
+                        hz_max: float = 8000.0):
+  """core.frequencies_softmax (core.py:424-457)."""
+  freqs = torch_float32(freqs, device=freqs.device if torch.is_tensor(freqs) else 'cpu')
+  if freqs.dim() == 3:
+    freqs = _add_depth_axis(freqs, depth)
+  else:
+    depth = int(freqs.shape[-1])
+  f_probs = torch.softmax(freqs, dim=-1)
+  unit_bins = torch.linspace(0.0, 1.0, depth, device=freqs.device)
+  unit_bins = unit_bins[None, None, None, :]
+  f_unit = torch.sum(unit_bins * f_probs, dim=-1)
+  return unit_to_hz(f_unit, hz_min=hz_min, hz_max=hz_max)
+
+
+def frequencies_sigmoid(freqs, depth: int = 1, hz_min: float = 0.0,
+                        hz_max: float = 8000.0):
+  """core.frequencies_sigmoid (core.py:460-507): a sum of `depth` sigmoids, each
+  mapped logarithmically onto a slice of [hz_min, hz_max]."""
+  freqs = torch_float32(freqs, device=freqs.device if torch.is_tensor(freqs) else 'cpu')
+  if freqs.dim() == 3:
+    freqs = _add_depth_axis(freqs, depth)
+  else:
+    depth = int(freqs.shape[-1])
+  f_probs = torch.sigmoid(freqs)
+  hz_scales = []
+  hz_min_copy = hz_min
+  remainder = hz_max - hz_min
+  scale_factor = remainder**(1.0 / depth)
+  for i in range(depth):
+    if i == (depth - 1):
+      hz_max = remainder
+      hz_min = hz_min_copy
+    else:
+      hz_max = remainder * (1.0 - 1.0 / scale_factor)
+      hz_min = 0
+      remainder -= hz_max
+    hz_scales.append(unit_to_hz(f_probs[..., i], hz_min=hz_min, hz_max=hz_max))
+  return torch.sum(torch.stack(hz_scales, dim=-1), dim=-1)
+
+
+# ----------------------------------------------------------------------------
 # Resampling (core.py:573-714) - stand-alone ops (the synthesizers fuse them)
 # ----------------------------------------------------------------------------
 _RESAMPLE_METHODS = {'window': 0, 'linear': 1, 'nearest': 2}
@@ -453,6 +563,34 @@ def _crop_range(total_size, audio_size, ir_size, padding, delay_compensation):
   return start, len(rng), crop_size
 
 
+# Impulse responses longer than this take the FFT formulation (cuFFT through
+# torch.fft) instead of the direct-form FIR kernel: the direct form costs
+# audio_size * ir_size MACs per item, the framed FFT convolution O(N log N) - the
+# cross-over is a few thousand taps.  This is the Reverb case (48000-tap IR,
+# effects.py:28-117).
+FFT_CONVOLVE_MIN_IR = 2048
+
+
+def _fft_convolve_cufft(audio, impulse_response, n_ir_frames, frame_size, fft_size,
+                        start, crop_size):
+  """The reference's own algorithm (core.py:1445-1473) on torch.fft: frame (hop =
+  frame_size, zero padded), rfft both, multiply, irfft, overlap-add, crop."""
+  b, n = audio.shape
+  pad = n_ir_frames * frame_size - n
+  frames = torch.nn.functional.pad(audio, (0, pad)).reshape(b, n_ir_frames, frame_size)
+  audio_fft = torch.fft.rfft(frames, n=fft_size, dim=-1)
+  ir_fft = torch.fft.rfft(impulse_response, n=fft_size, dim=-1)   # broadcasts batch 1
+  frames_out = torch.fft.irfft(audio_fft * ir_fft, n=fft_size, dim=-1)
+  if n_ir_frames == 1:
+    total = frames_out[:, 0, :]
+  else:
+    total_size = (n_ir_frames - 1) * frame_size + fft_size
+    total = torch.nn.functional.fold(
+        frames_out.transpose(1, 2), output_size=(total_size, 1),
+        kernel_size=(fft_size, 1), stride=(frame_size, 1))[:, 0, :, 0]
+  return total[:, start:start + crop_size].contiguous()
+
+
 def fft_convolve(audio, impulse_response, padding: Text = 'same',
                  delay_compensation: int = -1, out=None, accumulate=False):
   """core.fft_convolve (core.py:1382-1473).
@@ -497,6 +635,16 @@ def fft_convolve(audio, impulse_response, padding: Text = 'same',
         f'(start={start}, total={total_size}, crop={crop_size}).')
   audio = torch_float32(audio)
   impulse_response = torch_float32(impulse_response).reshape(si)
+  if ir_size >= FFT_CONVOLVE_MIN_IR:
+    wet = _fft_convolve_cufft(audio, impulse_response, n_ir_frames, frame_size,
+                              fft_size, int(start), int(crop_size))
+    if out is None:
+      return wet
+    if accumulate:
+      out += wet
+    else:
+      out.copy_(wet)
+    return out
   if out is None:
     out = torch.empty((batch_size, crop_size), dtype=torch.float32,
                       device=audio.device)

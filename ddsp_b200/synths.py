@@ -107,3 +107,48 @@ class FilteredNoise(processors.Processor):
         magnitudes, self.n_samples, window_size=self.window_size, noise=noise,
         seed=self.seed, offset=self.next_offset(), out=out,
         accumulate=accumulate)
+
+
+class Sinusoidal(processors.Processor):
+  """Bank of arbitrary sinusoidal oscillators (synths.py:260-323).
+
+  get_controls is frame-rate torch arithmetic; get_signal resamples both
+  controls to audio rate (`ddsp_b200_resample`) and runs `ddsp_b200_oscillator_bank`
+  (exact wrapped phase, three-pass chunked scan) - the [batch, n_samples,
+  n_sinusoids] envelopes are materialised here, as in the reference: this
+  processor is outside the fused decoder path."""
+
+  def __init__(self,
+               n_samples=64000,
+               sample_rate=16000,
+               amp_scale_fn=core.exp_sigmoid,
+               amp_resample_method='window',
+               freq_scale_fn=core.frequencies_sigmoid,
+               name='sinusoidal'):
+    super().__init__(name=name)
+    self.n_samples = n_samples
+    self.sample_rate = sample_rate
+    self.amp_scale_fn = amp_scale_fn
+    self.amp_resample_method = amp_resample_method
+    self.freq_scale_fn = freq_scale_fn
+
+  def get_controls(self, amplitudes, frequencies):
+    """synths.py:277-303."""
+    amplitudes = core.torch_float32(amplitudes)
+    frequencies = core.torch_float32(frequencies)
+    if self.amp_scale_fn is not None:
+      amplitudes = self.amp_scale_fn(amplitudes)
+    if self.freq_scale_fn is not None:
+      frequencies = self.freq_scale_fn(frequencies)
+      amplitudes = core.remove_above_nyquist(frequencies, amplitudes,
+                                             self.sample_rate)
+    return {'amplitudes': amplitudes, 'frequencies': frequencies}
+
+  def get_signal(self, amplitudes, frequencies):
+    """synths.py:305-323."""
+    amplitude_envelopes = core.resample(amplitudes, self.n_samples,
+                                        method=self.amp_resample_method)
+    frequency_envelopes = core.resample(frequencies, self.n_samples)
+    return core.oscillator_bank(frequency_envelopes=frequency_envelopes,
+                                amplitude_envelopes=amplitude_envelopes,
+                                sample_rate=self.sample_rate)

@@ -657,3 +657,74 @@ def philox_uniform_noise(batch_size, n_samples, seed, offset=0):
   bits = (r >> np.uint32(9)) | np.uint32(0x3F800000)
   f = bits.view(np.float32)
   return (np.float32(2.0) * f - np.float32(3.0)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------
+# Frequency scaling of network outputs and the Sinusoidal synth
+# (core.py:219-348, 414-507; synths.py:260-323)
+# ----------------------------------------------------------------------------
+def logb(x, base=2.0, eps=1e-5, dtype=np.float64):
+  """core.logb (core.py:219-221)."""
+  return safe_divide(safe_log(np.asarray(x, dtype), eps),
+                     safe_log(np.asarray(base, dtype), eps), eps)
+
+
+def midi_to_hz(notes, dtype=np.float64):
+  """core.midi_to_hz (core.py:280-297)."""
+  return 440.0 * (2.0 ** ((np.asarray(notes, dtype) - 69.0) / 12.0))
+
+
+def hz_to_midi(frequencies, dtype=np.float64):
+  """core.hz_to_midi (core.py:300-306)."""
+  f = np.asarray(frequencies, dtype)
+  notes = 12.0 * (logb(f, 2.0, dtype=dtype) - logb(440.0, 2.0, dtype=dtype)) + 69.0
+  return np.where(f <= 0.0, 0.0, notes)
+
+
+def unit_to_hz(unit, hz_min, hz_max, dtype=np.float64):
+  """core.unit_to_hz / unit_to_midi (core.py:309-336), clip=False."""
+  midi_min, midi_max = hz_to_midi(hz_min, dtype), hz_to_midi(hz_max, dtype)
+  return midi_to_hz(midi_min + (midi_max - midi_min) * np.asarray(unit, dtype), dtype)
+
+
+def frequencies_sigmoid(freqs, depth=1, hz_min=0.0, hz_max=8000.0, dtype=np.float64):
+  """core.frequencies_sigmoid (core.py:460-507)."""
+  freqs = np.asarray(freqs, dtype)
+  if freqs.ndim == 3:
+    b, t, c = freqs.shape
+    freqs = freqs.reshape(b, t, c // depth, depth)
+  else:
+    depth = freqs.shape[-1]
+  f_probs = 1.0 / (1.0 + np.exp(-freqs))
+  hz_scales = []
+  hz_min_copy = hz_min
+  remainder = hz_max - hz_min
+  scale_factor = remainder**(1.0 / depth)
+  for i in range(depth):
+    if i == depth - 1:
+      hz_max = remainder
+      hz_min = hz_min_copy
+    else:
+      hz_max = remainder * (1.0 - 1.0 / scale_factor)
+      hz_min = 0
+      remainder -= hz_max
+    hz_scales.append(unit_to_hz(f_probs[..., i], hz_min, hz_max, dtype))
+  return np.sum(np.stack(hz_scales, axis=-1), axis=-1)
+
+
+def sinusoidal_get_controls(amplitudes, frequencies, sample_rate=16000, depth=1,
+                            dtype=np.float64):
+  """synths.Sinusoidal.get_controls (synths.py:277-303), default scale fns."""
+  amps = exp_sigmoid(np.asarray(amplitudes, dtype))
+  freqs = frequencies_sigmoid(frequencies, depth=depth, dtype=dtype)
+  amps = remove_above_nyquist(freqs, amps, sample_rate)
+  return {'amplitudes': amps, 'frequencies': freqs}
+
+
+def sinusoidal_get_signal(amplitudes, frequencies, n_samples, sample_rate=16000,
+                          amp_resample_method='window', dtype=np.float64):
+  """synths.Sinusoidal.get_signal (synths.py:305-323)."""
+  amp_env = resample(np.asarray(amplitudes, dtype), n_samples,
+                     method=amp_resample_method)
+  freq_env = resample(np.asarray(frequencies, dtype), n_samples)
+  return oscillator_bank(freq_env, amp_env, sample_rate=sample_rate, dtype=dtype)

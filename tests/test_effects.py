@@ -1,0 +1,94 @@
+"""Reverb / FIRFilter and the long-impulse-response path of
+core.fft_convolve (framed FFT convolution on torch.fft / cuFFT).
+
+CPU: the FFT formulation against the oracle's literal restatement of
+core.py:1382-1473, for single-frame (reverb) and multi-frame IRs.  GPU: the
+processors against the float64 oracle through both routes of fft_convolve."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddsp_oracle as o
+from ddsp_b200 import core
+
+
+def _fft_path(audio, ir, padding, delay):
+  b, n = audio.shape
+  ir3 = ir if ir.ndim == 3 else ir[:, None, :]
+  f, s = ir3.shape[1], ir3.shape[2]
+  frame = int(np.ceil(n / f))
+  fft_size = core.get_fft_size(frame, s, power_of_2=True)
+  total = (f - 1) * frame + fft_size
+  start, out_len, crop = core._crop_range(total, n, s, padding, delay)
+  assert out_len == crop
+  return core._fft_convolve_cufft(torch.from_numpy(audio), torch.from_numpy(ir3), f,
+                                  frame, fft_size, int(start), int(crop)).numpy()
+
+
+@pytest.mark.parametrize('n,frames,taps,padding,delay', [
+    (4000, 1, 3000, 'same', 0), (4000, 1, 3000, 'same', -1), (1000, 1, 100, 'valid', -1),
+    (1280, 20, 129, 'same', -1), (1280, 5, 300, 'valid', -1), (999, 1, 4096, 'same', 0)])
+def test_fft_formulation_matches_oracle(n, frames, taps, padding, delay):
+  rng = np.random.default_rng(n + taps)
+  audio = rng.standard_normal((2, n)).astype(np.float32)
+  ir = (rng.standard_normal((2, frames, taps)) / np.sqrt(taps)).astype(np.float32)
+  want = o.fft_convolve(audio, ir, padding=padding, delay_compensation=delay)
+  got = _fft_path(audio, ir, padding, delay)
+  assert got.shape == want.shape
+  assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+
+
+def test_reverb_value_errors_and_masking():
+  """effects.py:81-101 (ValueError without an IR) and 50-59 (dry tap masked)."""
+  from ddsp_b200 import effects
+  rev = effects.Reverb(trainable=False)
+  ir = torch.arange(1.0, 6.0)[None, :].repeat(2, 1)
+  masked = rev._mask_dry_ir(ir)
+  assert masked.tolist() == [[0.0, 2.0, 3.0, 4.0, 5.0]] * 2
+  assert rev._mask_dry_ir(ir[..., None]).shape == (2, 5)
+  assert rev._match_dimensions(torch.zeros(3, 10), torch.ones(4)).shape == (3, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('taps,add_dry', [(3000, True), (48000, False), (200, True)])
+def test_reverb_matches_oracle(taps, add_dry):
+  import ddsp_b200
+  from tests.util import rel_err
+  rng = np.random.default_rng(taps)
+  B, N = 2, 16000
+  audio = rng.standard_normal((B, N)).astype(np.float32)
+  ir = (rng.standard_normal((B, taps)) * np.exp(-np.arange(taps) / (taps / 6.0)) /
+        np.sqrt(taps)).astype(np.float32)
+  rev = ddsp_b200.Reverb(add_dry=add_dry)
+  with pytest.raises(ValueError):
+    rev.get_controls(audio)
+  got = rev(audio, ir).cpu().numpy()
+  masked = ir.copy()
+  masked[:, 0] = 0.0
+  want = o.fft_convolve(audio, masked, padding='same', delay_compensation=0)
+  if add_dry:
+    want = want + audio
+  assert got.shape == (B, N)
+  emax, el2 = rel_err(got, want)
+  assert emax < 1e-4 and el2 < 1e-4, (emax, el2)
+
+
+@pytest.mark.gpu
+def test_trainable_reverb_and_fir_filter():
+  import ddsp_b200
+  from tests.util import rel_err
+  rng = np.random.default_rng(3)
+  B, N, F, nb = 2, 6400, 100, 65
+  audio = rng.standard_normal((B, N)).astype(np.float32)
+  rev = ddsp_b200.Reverb(trainable=True, reverb_length=4000)
+  out = rev(audio)
+  assert tuple(out.shape) == (B, N) and rev._ir.requires_grad
+  out.square().mean().backward()
+  assert rev._ir.grad is not None and float(rev._ir.grad.abs().sum()) > 0
+  mags = rng.standard_normal((B, F, nb)).astype(np.float32)
+  filt = ddsp_b200.FIRFilter(window_size=257)
+  got = filt(audio, mags).cpu().numpy()
+  scaled = o.exp_sigmoid(mags.astype(np.float64))
+  want = o.frequency_filter(audio, scaled, window_size=257)
+  emax, el2 = rel_err(got, want)
+  assert emax < 1e-4 and el2 < 1e-4, (emax, el2)
