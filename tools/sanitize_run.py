@@ -38,7 +38,19 @@ raw = {k: feats[k].clone().requires_grad_(True) for k in
 audio = ag.decoder_train(raw['amps'], raw['harmonic_distribution'], feats['f0_hz'],
                          raw['noise_magnitudes'], n_samples=N, window_size=0)
 audio.square().mean().backward()
+# fused spectral-loss pieces, host-buffer pipeline, Sinusoidal, Reverb (cuFFT route)
+from ddsp_b200 import losses, host
+tgt = 0.1 * torch.randn(B, N, device='cuda')
+aud = (0.1 * torch.randn(B, N, device='cuda')).requires_grad_(True)
+losses.SpectralLoss(fft_sizes=(256, 64), mag_weight=1.0, logmag_weight=1.0)(tgt, aud).backward()
+dec = ddsp_b200.HostDecoder(group, B, F, K, nb, n_chunks=2)
+e = dec({k: host.pin(inp[k]) for k in ['amps', 'harmonic_distribution', 'f0_hz',
+                                        'noise_magnitudes']})
+dec.close()
+f = ddsp_b200.Sinusoidal(n_samples=640)(torch.randn(2, 10, 6), torch.randn(2, 10, 6))
+g = ddsp_b200.Reverb()(torch.randn(2, 3000).cuda(), 0.01 * torch.randn(2, 2500).cuda())
 torch.cuda.synchronize()
+assert torch.isfinite(e).all() and torch.isfinite(f).all() and torch.isfinite(g).all()
 print('sanitize_run ok', float(a.abs().mean()), float(b.abs().mean()),
       float(c.abs().mean()), float(d.abs().mean()),
       float(raw['harmonic_distribution'].grad.abs().mean()))
