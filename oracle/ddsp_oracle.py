@@ -712,6 +712,21 @@ def frequencies_sigmoid(freqs, depth=1, hz_min=0.0, hz_max=8000.0, dtype=np.floa
   return np.sum(np.stack(hz_scales, axis=-1), axis=-1)
 
 
+def frequencies_softmax(freqs, depth=1, hz_min=20.0, hz_max=8000.0, dtype=np.float64):
+  """core.frequencies_softmax (core.py:424-457)."""
+  freqs = np.asarray(freqs, dtype)
+  if freqs.ndim == 3:
+    b, t, c = freqs.shape
+    freqs = freqs.reshape(b, t, c // depth, depth)
+  else:
+    depth = freqs.shape[-1]
+  e = np.exp(freqs - freqs.max(axis=-1, keepdims=True))
+  f_probs = e / e.sum(axis=-1, keepdims=True)
+  unit_bins = np.linspace(0.0, 1.0, depth)[None, None, None, :]
+  f_unit = np.sum(unit_bins * f_probs, axis=-1)
+  return unit_to_hz(f_unit, hz_min, hz_max, dtype)
+
+
 def sinusoidal_get_controls(amplitudes, frequencies, sample_rate=16000, depth=1,
                             dtype=np.float64):
   """synths.Sinusoidal.get_controls (synths.py:277-303), default scale fns."""

@@ -21,6 +21,17 @@ def test_frequencies_sigmoid_matches_oracle(depth):
   np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-2)
 
 
+@pytest.mark.parametrize('depth', [2, 16])
+def test_frequencies_softmax_matches_oracle(depth):
+  rng = np.random.default_rng(10 + depth)
+  x = rng.normal(0, 2, (2, 5, 3 * depth)).astype(np.float32)
+  got = core.frequencies_softmax(torch.from_numpy(x), depth=depth).numpy()
+  want = o.frequencies_softmax(x, depth=depth)
+  assert got.shape == want.shape == (2, 5, 3)
+  np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-2)
+  assert (got >= 20.0 - 1e-3).all() and (got <= 8000.0 + 1.0).all()
+
+
 def test_frequencies_controls_are_bounded():
   """synths_test.py:89-110: 0 <= f <= 8000 Hz for any network output."""
   depth = 10
