@@ -122,8 +122,9 @@ def exp_sigmoid(x, exponent=10.0, max_value=2.0, threshold=1e-7):
 # torch ops (a few thousand elements per item), device-agnostic.
 # ----------------------------------------------------------------------------
 def _as_f32(x):
-  return x.to(torch.float32) if torch.is_tensor(x) else torch.tensor(
-      x, dtype=torch.float32)
+  if torch.is_tensor(x):
+    return x.to(torch.float32)
+  return torch.as_tensor(np.asarray(x, dtype=np.float32))
 
 
 def safe_log(x, eps=1e-5):
@@ -157,13 +158,14 @@ def hz_to_midi(frequencies):
 
 def unit_to_midi(unit, midi_min=20.0, midi_max=90.0, clip: bool = False):
   """core.unit_to_midi (core.py:309-315)."""
+  unit = _as_f32(unit)
   unit = torch.clamp(unit, 0.0, 1.0) if clip else unit
   return midi_min + (midi_max - midi_min) * unit
 
 
 def midi_to_unit(midi, midi_min=20.0, midi_max=90.0, clip: bool = False):
   """core.midi_to_unit (core.py:318-324)."""
-  unit = (midi - midi_min) / (midi_max - midi_min)
+  unit = (_as_f32(midi) - midi_min) / (midi_max - midi_min)
   return torch.clamp(unit, 0.0, 1.0) if clip else unit
 
 

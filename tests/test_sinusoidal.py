@@ -90,3 +90,45 @@ def test_sinusoidal_output_shape():
   synth = ddsp_b200.Sinusoidal(n_samples=32000, sample_rate=16000)
   out = synth(np.zeros((3, 1000, 10), np.float32), np.zeros((3, 1000, 10), np.float32))
   assert tuple(out.shape) == (3, 32000)
+
+
+# ---- ports of core_test.py:27-92 (UtilitiesTest); librosa's two formulas are
+# hz = 440 * 2^((m - 69) / 12) and m = 12 (log2 hz - log2 440) + 69 ----------------
+def test_midi_to_hz_is_accurate():
+  midi = np.arange(128)
+  want = 440.0 * 2.0 ** ((midi - 69.0) / 12.0)
+  np.testing.assert_allclose(core.midi_to_hz(midi).numpy(), want, rtol=1e-5)
+
+
+def test_hz_to_midi_is_accurate():
+  hz = np.linspace(0.0, 20000.0, 128)
+  with np.errstate(divide='ignore'):
+    want = 12.0 * (np.log2(hz) - np.log2(440.0)) + 69.0
+  want = np.where(hz <= 0.0, 0.0, want)
+  np.testing.assert_allclose(core.hz_to_midi(hz).numpy(), want, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize('clip', [True, False])
+def test_midi_unit_maps_are_accurate(clip):
+  midi_min, midi_max = 20.0, 90.0
+  midi = np.linspace(0.0, 127.0, 1000)
+  want = (midi - midi_min) / (midi_max - midi_min)
+  want = np.clip(want, 0.0, 1.0) if clip else want
+  np.testing.assert_allclose(
+      core.midi_to_unit(midi, midi_min=midi_min, midi_max=midi_max, clip=clip).numpy(),
+      want, rtol=1e-5, atol=1e-6)
+  unit = np.linspace(-1.0, 2.0, 1000)
+  want = np.clip(unit, 0.0, 1.0) if clip else unit
+  want = midi_min + (midi_max - midi_min) * want
+  np.testing.assert_allclose(
+      core.unit_to_midi(unit, midi_min=midi_min, midi_max=midi_max, clip=clip).numpy(),
+      want, rtol=1e-5, atol=1e-4)
+
+
+def test_unit_hz_maps_are_accurate():
+  hz_min, hz_max = 20.0, 1000.0
+  unit = np.linspace(0.0, 1.0, 128)
+  hz = np.logspace(np.log10(hz_min), np.log10(hz_max), 128)
+  np.testing.assert_allclose(core.unit_to_hz(unit, hz_min, hz_max).numpy(), hz, rtol=1e-4)
+  np.testing.assert_allclose(core.hz_to_unit(hz, hz_min, hz_max).numpy(), unit,
+                             rtol=1e-4, atol=1e-5)
