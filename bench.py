@@ -5,12 +5,17 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
       --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], per GPU): batch 32 x 64000 samples @16 kHz,
-F=1000 frames, K=100 harmonics, 65 noise bands - the `ae.gin` DAG
-Harmonic -> FilteredNoise -> Add, from raw network outputs (get_controls
-included), through ddsp_b200.ProcessorGroup.  One "step" = one decoder forward
-over one batch.  Weak scaling: every GPU runs the same per-GPU batch on its own
-shard, no data-path collective.
+Workload per GPU: batch 256 x 64000 samples @16 kHz, F=1000 frames, K=100
+harmonics, 65 noise bands - BASELINE.json configs[2] at N=1 and configs[4]
+(2048 = 256/GPU) at N=8 - the `ae.gin` DAG Harmonic -> FilteredNoise -> Add, from
+raw network outputs (get_controls included), through ddsp_b200.ProcessorGroup.
+One "step" = one decoder forward over one batch, replayed from a CUDA graph
+captured around the public ProcessorGroup call (no Python between the kernels of
+the timed region).  Weak scaling: every GPU runs the same per-GPU batch on its
+own shard, no data-path collective; the optional NCCL all-gather
+of the audio is timed separately and reported as `all_gather`.  configs[1]
+(B=32), configs[0] (Harmonic only, B=1) and configs[3] (forward + backward
+through SpectralLoss, B=128) ride along as extra keys timed on rank 0.
 
 One JSON line on stdout (rank 0).  See the task contract for the keys.
 """
@@ -33,7 +38,7 @@ N_FRAMES = 1000
 N_HARM = 100
 N_BANDS = 65
 SAMPLE_RATE = 16000
-BATCH_PER_GPU = 32
+BATCH_PER_GPU = 256
 L2_BYTES = 126 * 1024 * 1024
 
 # Algorithmic bytes per batch item (BASELINE.md section 3 / SURVEY.md 8d), fp32.
@@ -188,12 +193,28 @@ def cpu_reference_throughput(items, repeats=1, threads=None):
   return items * N_SAMPLES / best, best, torch.get_num_threads()
 
 
+def cpu_c1_throughput(c1):
+  """configs[0] (Harmonic only, B=1, 16000 samples, 64 harmonics) on the CPU port."""
+  import torch
+  from oracle import ref_port_torch as rp
+  torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+  t = {k: torch.from_numpy(c1[k]) for k in ('amps', 'harmonic_distribution', 'f0_hz')}
+  best = None
+  for _ in range(5):
+    t0 = time.perf_counter()
+    a, h = rp.harmonic_controls(t['amps'], t['harmonic_distribution'], t['f0_hz'])
+    rp.harmonic_signal(a, h, t['f0_hz'], 16000)
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+  return 16000 / best
+
+
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return None  # other ranks exit 0 without work
   import torch
-  # bounded sample of the B=32 workload: up to 8 items per step, fewer when the
+  # bounded sample of the B=256 workload: up to 8 items per step, fewer when the
   # caller asks for many steps, so that warm-up + timed steps stay near 2.5 min
   # (one item costs up to ~0.65 s on this class of host)
   n_calls = args.warmup + args.steps
@@ -213,13 +234,17 @@ def run_reference(args):
       'ms_per_step': 1e3 * sum(times) / len(times), 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': 'ae.gin decoder Harmonic(100)+FilteredNoise(65)+Add, '
-                             'N=64000 @16kHz, F=1000 (configs[1] shapes)',
-                 'batch_per_step': items},
+                             'N=64000 @16kHz, F=1000 (configs[2] shapes); each step is '
+                             'a bounded sample of %d of the 256 batch items - '
+                             'throughput is per sample, so it compares directly' % items,
+                 'batch_per_step': items, 'batch_per_gpu': BATCH_PER_GPU},
       'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores,
                        'kind': 'port',
-                       'sample': '%d of the 32 batch items per step (torch-CPU '
-                                 'op-by-op float32 port of ddsp core/synths; '
-                                 'TensorFlow is not installable here)' % items},
+                       'sample': '%d of the 256 batch items per step (torch-CPU '
+                                 'op-by-op float32 port of ddsp core/synths, '
+                                 'validated against the unmodified reference run '
+                                 'on oracle/tf_shim; TensorFlow is not installable '
+                                 'here)' % items},
       'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
@@ -234,7 +259,7 @@ def run_ours(args):
   import torch
   import torch.distributed as dist
   import ddsp_b200
-  from ddsp_b200 import _lib, core
+  from ddsp_b200 import _lib, core, host as host_mod, sharding
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
@@ -243,21 +268,28 @@ def run_ours(args):
     raise SystemExit('bench.py (ours) needs a CUDA device; there is no CPU path.')
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
+  # Pin this process to the CPUs of the GPU's NUMA node BEFORE any page-locked
+  # buffer exists: pinned pages are placed where the allocating thread runs, and on
+  # a two-socket 8-GPU host a far-socket buffer halves the host<->device rate.
+  numa_node = host_mod.bind_to_device_numa_node(dev)
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     import datetime
     dist.init_process_group('nccl', device_id=dev,
-                            timeout=datetime.timedelta(seconds=180))
+                            timeout=datetime.timedelta(seconds=300))
   lib = _lib.load()
   B = args.batch
 
-  harm = ddsp_b200.Harmonic(n_samples=N_SAMPLES, sample_rate=SAMPLE_RATE)
-  noise = ddsp_b200.FilteredNoise(n_samples=N_SAMPLES, window_size=0, seed=rank)
-  add = ddsp_b200.Add()
-  group = ddsp_b200.ProcessorGroup(dag=[
-      (harm, ['amps', 'harmonic_distribution', 'f0_hz']),
-      (noise, ['noise_magnitudes']),
-      (add, ['filtered_noise/signal', 'harmonic/signal'])])
+  def make_group(seed):
+    harm = ddsp_b200.Harmonic(n_samples=N_SAMPLES, sample_rate=SAMPLE_RATE)
+    noise = ddsp_b200.FilteredNoise(n_samples=N_SAMPLES, window_size=0, seed=seed)
+    add = ddsp_b200.Add()
+    return harm, noise, ddsp_b200.ProcessorGroup(dag=[
+        (harm, ['amps', 'harmonic_distribution', 'f0_hz']),
+        (noise, ['noise_magnitudes']),
+        (add, ['filtered_noise/signal', 'harmonic/signal'])])
+
+  harm, noise, group = make_group(rank)
 
   # A ring of distinct input sets larger than 2x L2 so every step reads HBM.
   host = make_host_inputs(B, seed=1234 + rank)
@@ -305,8 +337,45 @@ def run_ours(args):
     return ms
 
   # -- value: whole decoder step, inputs resident in HBM ----------------------
-  def step_resident(i):
-    group(dev_sets[i % n_sets])
+  # The step is the public call `group(inputs)` (ProcessorGroup.__call__ over raw
+  # network outputs).  It is captured once per input set in a CUDA graph
+  # (torch.cuda.graph around that same call, the route a serving loop would take)
+  # so that the timed region replays kernels back to back with no Python, ctypes
+  # or allocator work between them; --graph 0 times the eager call instead.
+  graph_note = 'eager ProcessorGroup.__call__'
+  launches_per_step = None
+  graphs, graph_out = [], []
+  if args.graph:
+    try:
+      side = torch.cuda.Stream()
+      side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(side):
+        for d in dev_sets:
+          group(d)
+      torch.cuda.current_stream().wait_stream(side)
+      torch.cuda.synchronize()
+      for d in dev_sets:
+        g = torch.cuda.CUDAGraph()
+        c0 = lib.ddsp_b200_launch_count()
+        with torch.cuda.graph(g, stream=side):
+          o = group(d)
+        launches_per_step = int(lib.ddsp_b200_launch_count() - c0)
+        graphs.append(g)
+        graph_out.append(o)
+      torch.cuda.synchronize()
+      graph_note = ('CUDA graph replay of ProcessorGroup.__call__ (one graph per '
+                    'input set, %d kernel nodes each)' % launches_per_step)
+    except Exception as e:  # pylint: disable=broad-except
+      graphs, graph_out = [], []
+      graph_note = 'eager ProcessorGroup.__call__ (graph capture failed: %r)' % (e,)
+      torch.cuda.synchronize()
+
+  if graphs:
+    def step_resident(i):
+      graphs[i % n_sets].replay()
+  else:
+    def step_resident(i):
+      group(dev_sets[i % n_sets])
 
   sampler = ClockSampler(local_rank)
   if rank == 0:
@@ -314,8 +383,11 @@ def run_ours(args):
   c0 = lib.ddsp_b200_launch_count()
   ms_total = timed(step_resident, args.steps, args.warmup,
                    mark=sampler if rank == 0 else None)
-  launches = lib.ddsp_b200_launch_count() - c0
-  launches_timed = launches * args.steps // (args.steps + args.warmup)
+  if graphs:
+    launches_timed = launches_per_step * args.steps
+  else:
+    launches = lib.ddsp_b200_launch_count() - c0
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
   ms_per_step = ms_total / args.steps
   value = world * B * N_SAMPLES / (ms_per_step * 1e-3)
 
@@ -330,7 +402,7 @@ def run_ours(args):
   # The PCIe link and copy engines need ~50 ms of traffic to reach full speed
   # after idling (first copies of a run move at about half rate): warm them up,
   # then pick the chunk count on this box (rank-local, short) before timing.
-  cand = [args.chunks] if args.chunks > 0 else [2, 3, 4]
+  cand = [args.chunks] if args.chunks > 0 else ([2, 3, 4] if B <= 64 else [4, 6, 8])
   decs = {c: ddsp_b200.HostDecoder(group, max_batch=B, n_frames=N_FRAMES,
                                    n_harmonics=N_HARM, n_bands=N_BANDS, n_chunks=c)
           for c in cand}
@@ -339,13 +411,20 @@ def run_ours(args):
     decs[cand[0]](pinned, out=out_host, sync=True)
   best_c, best_ms = cand[0], None
   for c in cand:
-    ms = timed(step_e2e_with(decs[c]), 20, 3, collective=False) / 20
+    ms = timed(step_e2e_with(decs[c]), 8, 2, collective=False) / 8
     if best_ms is None or ms < best_ms:
       best_c, best_ms = c, ms
   host_dec = decs[best_c]
-  e2e_steps = max(args.steps, 20)
-  ms_e2e = timed(step_e2e_with(host_dec), e2e_steps, max(3, args.warmup)) / e2e_steps
+  e2e_steps = max(min(args.steps, 30), 10)
+  ms_e2e = timed(step_e2e_with(host_dec), e2e_steps, 3) / e2e_steps
   e2e_value = world * B * N_SAMPLES / (ms_e2e * 1e-3)
+
+  # link floor of the same round trip: the H2D bytes alone, pinned -> device,
+  # one copy per tensor (nothing else on the link), to say how far e2e is from it
+  def step_h2d_only(i):
+    for k, v in pinned.items():
+      dev_sets[0][k].copy_(v, non_blocking=True)
+  ms_h2d_floor = timed(step_h2d_only, 10, 3, collective=False) / 10
 
   # the same round trip without the pipeline (4 copies, one call, one copy)
   def step_e2e_serial(i):
@@ -354,7 +433,21 @@ def run_ours(args):
     out_host.copy_(audio, non_blocking=True)
     torch.cuda.current_stream().synchronize()
 
-  ms_e2e_serial = timed(step_e2e_serial, e2e_steps, 3) / e2e_steps
+  ms_e2e_serial = timed(step_e2e_serial, 5, 2, collective=False) / 5
+  for d in decs.values():
+    d.close()
+
+  # -- optional reassembly: NCCL all-gather of the [B, N] audio shards ---------
+  all_gather = None
+  if world > 1:
+    shard = graph_out[0] if graph_out else group(dev_sets[0])
+    def step_gather(i):
+      sharding.all_gather_audio(shard, B * world)
+    ms_ag = timed(step_gather, 10, 3) / 10
+    all_gather = {'ms': ms_ag, 'bytes_out_per_rank': 4 * B * world * N_SAMPLES,
+                  'algbw_GBps': 4 * B * world * N_SAMPLES / (ms_ag * 1e-3) / 1e9,
+                  'backend': 'nccl all_gather_into_tensor over NVLink, off the '
+                             'synthesis path (not in ms_per_step)'}
 
   # -- per-kernel durations for the roofline (rank 0 reports) -----------------
   ctl = []
@@ -416,20 +509,42 @@ def run_ours(args):
   ms_noise = kernel_ms(noise_only)
   ms_ctl = kernel_ms(controls_only, group=2)
   clocks = sampler.stop() if rank == 0 else None
+  del ctl, audio_bufs
 
-  # -- secondary workload: C3 (B=256) for context ------------------------------
+  # -- the other configs, for context (rank 0, rank-local) ---------------------
   extra = {}
   if args.extra and rank == 0:
     try:
-      B3 = 256
-      h3 = make_host_inputs(B3, seed=77)
-      d3 = {k: torch.from_numpy(v).to(dev) for k, v in h3.items()}
-      ms3 = timed(lambda i: group(d3), 10, 3, collective=False) / 10
-      extra['c3_batch256_samples_per_s'] = B3 * N_SAMPLES / (ms3 * 1e-3)
-      extra['c3_ms_per_step'] = ms3
-      del d3
+      # configs[1]: the same decoder at B=32
+      B2 = 32
+      h2 = make_host_inputs(B2, seed=77)
+      sets2 = []
+      for s in range(8):     # 8 x 37.8 MB > 2x L2
+        d = {k: torch.from_numpy(v).to(dev) for k, v in h2.items()}
+        d['amps'] = d['amps'] + 0.01 * s
+        sets2.append(d)
+      ms2 = timed(lambda i: group(sets2[i % 8]), 40, 8, collective=False) / 40
+      extra['c2_batch32_samples_per_s'] = B2 * N_SAMPLES / (ms2 * 1e-3)
+      extra['c2_ms_per_step'] = ms2
+      extra['c2_decoder_fused_frac'] = (BYTES_DECODER_FUSED * B2 / (ms2 * 1e-3) / 1e9
+                                        ) / _measured_peaks()[0]
+      del sets2
     except Exception as e:  # pylint: disable=broad-except
-      extra['c3_error'] = repr(e)
+      extra['c2_error'] = repr(e)
+    try:
+      # configs[0]: Harmonic only, B=1, 16000 samples, 64 harmonics, 250 frames
+      from tests.util import synth_inputs
+      c1 = synth_inputs(1, 250, 64, 65, 16000, seed=5)
+      h1 = ddsp_b200.Harmonic(n_samples=16000, sample_rate=SAMPLE_RATE)
+      a1 = [torch.from_numpy(c1[k]).to(dev) for k in
+            ('amps', 'harmonic_distribution', 'f0_hz')]
+      ms1 = timed(lambda i: h1(*a1), 50, 10, collective=False) / 50
+      extra['c1_harmonic_b1_ms_per_step'] = ms1
+      extra['c1_samples_per_s'] = 16000 / (ms1 * 1e-3)
+      if not args.no_cpu_baseline and world == 1:
+        extra['c1_cpu_port_samples_per_s'] = cpu_c1_throughput(c1)
+    except Exception as e:  # pylint: disable=broad-except
+      extra['c1_error'] = repr(e)
     try:
       # configs[3]: decoder forward + backward through the multi-scale
       # SpectralLoss (ae.gin:39-41), B=128 - context only, not the headline.
@@ -466,12 +581,15 @@ def run_ours(args):
 
   peak, peak_src = _measured_peaks()
   # DRAM traffic of the same kernels from one ncu --set full capture of this
-  # workload (profiles/r01_traffic_b32.json; null for any other batch size)
+  # workload (profiles/*traffic*.json; null for any other batch size)
   traffic = {}
-  tpath = os.path.join(ROOT, 'profiles', 'r01_traffic_b32.json')
-  if os.path.exists(tpath):
-    with open(tpath) as f:
-      traffic = {k: v for k, v in json.load(f).items() if v.get('batch') == B}
+  for name in ('r02_traffic_b256.json', 'r01_traffic_b32.json'):
+    tpath = os.path.join(ROOT, 'profiles', name)
+    if os.path.exists(tpath):
+      with open(tpath) as f:
+        traffic = {k: v for k, v in json.load(f).items() if v.get('batch') == B}
+      if traffic:
+        break
   dom_is_harm = ms_harm >= ms_noise
   dom_ms = ms_harm if dom_is_harm else ms_noise
   dom_bytes = (BYTES_HARMONIC if dom_is_harm else BYTES_NOISE + 4 * N_SAMPLES) * B
@@ -494,13 +612,17 @@ def run_ours(args):
 
   # -- cpu baseline: bounded sample of the same workload on the host cores ----
   cpu = None
-  if not args.no_cpu_baseline:
+  if not args.no_cpu_baseline and world == 1:
     items = 8
     rate, dt, cores = cpu_reference_throughput(items, repeats=2)
     cpu = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
            'sample': '%d of the %d batch items (torch-CPU op-by-op float32 port '
-                     'of ddsp core/synths, %.2f s)' % (items, B, dt)}
+                     'of ddsp core/synths, validated against the unmodified '
+                     'reference run on oracle/tf_shim; %.2f s)' % (items, B, dt)}
 
+  cfg_name = ('configs[4]: decoder batch %d sharded over %d B200 (%d per GPU)'
+              % (B * world, world, B)) if world > 1 else (
+                  'configs[2]: decoder batch %d on one B200' % B)
   line = {
       'metric': 'audio samples/sec (Harmonic+FilteredNoise decoder)',
       'value': value, 'unit': 'samples/s', 'n_gpus': world,
@@ -508,25 +630,31 @@ def run_ours(args):
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
       'dtype': 'f32', 'data': 'synthetic',
       'config': {
-          'workload': 'configs[1]: ae.gin decoder Harmonic(100)+FilteredNoise(65)'
-                      '+Add via ProcessorGroup (get_controls + get_signal), '
-                      'batch %d per GPU, N=64000 @16kHz, F=1000' % B,
+          'workload': cfg_name + ' - ae.gin Harmonic(100)+FilteredNoise(65)+Add via '
+                      'ProcessorGroup (get_controls + get_signal), N=64000 @16kHz, '
+                      'F=1000',
           'batch_per_gpu': B, 'global_batch': B * world,
+          'step': graph_note,
           'l2_policy': 'ring of %d distinct input/output sets (%.0f MB > 2x L2)'
                        % (n_sets, n_sets * set_bytes / 1e6),
           'noise': 'in-kernel Philox4x32-10', 'parallelism': 'batch-sharded replicas, no collective',
+          'numa_node': numa_node,
       },
       'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e,
               'h2d_bytes_per_step': h2d_bytes * world,
               'd2h_bytes_per_step': d2h_bytes * world,
               'api': 'ddsp_b200.HostDecoder(group)(pinned host inputs) -> pinned '
                      'host audio, %d chunks on 3 streams' % best_c,
-              'ms_per_step_unpipelined': ms_e2e_serial},
+              'ms_per_step_unpipelined': ms_e2e_serial,
+              'ms_h2d_alone': ms_h2d_floor,
+              'over_link_floor': ms_e2e / ms_h2d_floor},
       'gpu_launches': int(launches_timed),
       'clocks': clocks,
       'roofline': roofline,
       'cpu_baseline': cpu,
   }
+  if all_gather is not None:
+    line['all_gather'] = all_gather
   line.update(extra)
   if world > 1:
     dist.barrier()
@@ -558,12 +686,14 @@ def _main():
   ap.add_argument('--warmup', type=int, default=10)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--batch', type=int, default=BATCH_PER_GPU,
-                  help='batch items per GPU (configs[1] = 32)')
+                  help='batch items per GPU (configs[2] / configs[4] = 256)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--chunks', type=int, default=0,
                   help='chunks of the host-buffer (e2e) pipeline; 0 = pick among 2/3/4')
   ap.add_argument('--extra', type=int, default=1,
-                  help='also time the B=256 (configs[2]) step on rank 0')
+                  help='also time configs[1] / [0] / [3] on rank 0')
+  ap.add_argument('--graph', type=int, default=1,
+                  help='replay the step from a CUDA graph (0 = eager call)')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
   if args.impl == 'reference':

@@ -91,7 +91,7 @@ class HostDecoder:
   """
 
   def __init__(self, group, max_batch, n_frames, n_harmonics, n_bands,
-               n_chunks=8, device=None):
+               n_chunks=8, device=None, bind_numa=True):
     pat = group._decoder_pattern()  # pylint: disable=protected-access
     if pat is None:
       raise ValueError('HostDecoder needs the decoder DAG [Harmonic, '
@@ -112,6 +112,10 @@ class HostDecoder:
     self.device = torch.device('cuda', torch.cuda.current_device()
                                if device is None else torch.device(device).index)
     self._handle = ctypes.c_void_p()
+    # Page-locked buffers made after this point (pinned_empty / pin, the `out`
+    # of __call__) land on the GPU's own NUMA node; bind_numa=False leaves the
+    # calling thread's CPU affinity alone.
+    self.numa_node = bind_to_device_numa_node(self.device) if bind_numa else None
     with torch.cuda.device(self.device):
       _lib.check(_lib.load().ddsp_b200_host_pipeline_create(
           ctypes.byref(self._handle), self.max_batch, self.n_frames,

@@ -46,6 +46,7 @@ class ProcessorGroup(dags.DAGLayer):
   def __init__(self, dag: dags.DAG, **kwarg_processors):
     super().__init__(dag, **kwarg_processors)
     self.processor_names = self.module_names
+    self._pattern_cache = None    # (dag identity, result of _decoder_pattern)
 
   @property
   def processors(self):
@@ -88,6 +89,19 @@ class ProcessorGroup(dags.DAGLayer):
   def _decoder_pattern(self):
     """Returns (harmonic, noise, harmonic_keys, noise_keys) if the DAG is
     exactly [Harmonic(a,b,c), FilteredNoise(m), Add(two signals)], else None."""
+    key = (id(self.dag), len(self.dag))
+    if self._pattern_cache is not None and self._pattern_cache[0] == key:
+      mods = self._pattern_cache[1]
+      # the DAG is fixed at construction; only re-check what attribute
+      # assignment could have changed since (the modules themselves)
+      if all(getattr(self, n, None) is m for n, m in mods):
+        return self._pattern_cache[2]
+    pat = self._decoder_pattern_uncached()
+    self._pattern_cache = (key, [(node[0], getattr(self, node[0], None))
+                                 for node in self.dag], pat)
+    return pat
+
+  def _decoder_pattern_uncached(self):
     from ddsp_b200 import synths  # local import: synths imports this module
     if len(self.dag) != 3:
       return None
@@ -120,6 +134,9 @@ class ProcessorGroup(dags.DAGLayer):
     n_in = [core.nested_lookup(k, outputs) for k in n_keys]
     for k in ['training', 'mask']:
       kwargs.pop(k, None)
+    # one Philox offset per call, whichever route runs (so the noise stream of
+    # call i does not depend on whether the shape was inside the fused regime)
+    offset = noise.next_offset()
     if (harm.scale_fn is core.exp_sigmoid and noise.scale_fn is core.exp_sigmoid
         and not kwargs and len(h_in) == 3 and len(n_in) == 1):
       # raw network outputs -> audio in two launches, controls never hit HBM
@@ -130,12 +147,11 @@ class ProcessorGroup(dags.DAGLayer):
             amp_resample_method=harm.amp_resample_method,
             normalize_below_nyquist=harm.normalize_below_nyquist,
             window_size=noise.window_size, initial_bias=noise.initial_bias,
-            noise=noise.injected_noise, seed=noise.seed,
-            offset=noise.next_offset())
+            noise=noise.injected_noise, seed=noise.seed, offset=offset)
       except NotImplementedError:
         pass   # outside the fused regime: per-processor path below
     audio = harm.get_signal(**harm.get_controls(*h_in, **kwargs))
-    return noise.get_signal(out=audio, accumulate=True,
+    return noise.get_signal(out=audio, accumulate=True, offset=offset,
                             **noise.get_controls(*n_in, **kwargs))
 
 

@@ -99,14 +99,15 @@ class FilteredNoise(processors.Processor):
       magnitudes = core.torch_float32(magnitudes)
     return {'magnitudes': magnitudes}
 
-  def get_signal(self, magnitudes, noise=None, out=None, accumulate=False):
+  def get_signal(self, magnitudes, noise=None, out=None, accumulate=False,
+                 offset=None):
     """synths.py:181-196."""
     if noise is None:
       noise = self.injected_noise
     return core.filtered_noise(
         magnitudes, self.n_samples, window_size=self.window_size, noise=noise,
-        seed=self.seed, offset=self.next_offset(), out=out,
-        accumulate=accumulate)
+        seed=self.seed, offset=self.next_offset() if offset is None else offset,
+        out=out, accumulate=accumulate)
 
 
 class Sinusoidal(processors.Processor):
