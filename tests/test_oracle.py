@@ -336,20 +336,3 @@ def test_torch_port_matches_oracle():
                               inp['f0_hz'])
   np.testing.assert_allclose(h.numpy(), c['harmonic_distribution'], rtol=1e-4,
                              atol=1e-9)
-
-
-def test_oracle_matches_committed_golden():
-  """Regression anchor (tests/golden/make_golden.py): the float64 arbiter of the
-  GPU parity tests reproduces its committed vectors - configs[0] (Harmonic only,
-  B=1, 16000 samples, 64 harmonics, 250 frames) and a small decoder DAG."""
-  import os
-  from tests.golden import make_golden as mg
-  here = os.path.dirname(os.path.abspath(mg.__file__))
-  for name, fn in (('c1_harmonic', mg.c1_harmonic), ('decoder_small', mg.decoder_small)):
-    want = np.load(os.path.join(here, name + '.npz'))
-    got = fn()
-    assert set(want.files) == set(got)
-    for k in want.files:
-      np.testing.assert_allclose(np.asarray(got[k], np.float64),
-                                 np.asarray(want[k], np.float64), rtol=0, atol=2e-7,
-                                 err_msg=f'{name}/{k}')
