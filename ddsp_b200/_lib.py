@@ -72,6 +72,13 @@ SIGNATURES = {
     'ddsp_b200_oscillator_bank':
         (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
     'ddsp_b200_resample': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'ddsp_b200_angular_cumsum':
+        (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'ddsp_b200_oscillator_bank_tf_sequential':
+        (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp]),
+    'ddsp_b200_sinusoidal_workspace': (_sz, [_i, _i, _i]),
+    'ddsp_b200_sinusoidal_forward':
+        (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
     'ddsp_b200_add': (_i, [_vp, _vp, _vp, _i64, _vp]),
     'ddsp_b200_frame_window': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'ddsp_b200_frame_window_adjoint': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -46,6 +46,12 @@ class HarmonicSynthesisFn(torch.autograd.Function):
   def backward(ctx, grad_audio):
     f0_hz, amplitudes, hd = ctx.saved_tensors
     n_samples, sample_rate, method = ctx.cfg
+    if ctx.needs_input_grad[0]:
+      raise NotImplementedError(
+          'HarmonicSynthesisFn: f0_hz requires grad, but the gradient with respect '
+          'to the fundamental frequency is not built (the reference gets it from '
+          'TF autodiff through the phase cumsum).  Detach f0_hz, or differentiate '
+          'core.oscillator_bank-style torch ops for that path.')
     b, f, k = hd.shape
     grad_audio = grad_audio.contiguous().to(torch.float32)
     g0 = torch.empty_like(hd)

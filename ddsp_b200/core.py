@@ -98,6 +98,52 @@ def _stream():
   return torch.cuda.current_stream().cuda_stream
 
 
+class _on_device_of:
+  """Context: make the device of the operands current (so the launch goes to
+  THAT device's current stream), after checking they all live on one device."""
+
+  def __init__(self, *tensors):
+    devs = {t.device for t in tensors if isinstance(t, torch.Tensor)}
+    if len(devs) > 1:
+      raise ValueError('ddsp_b200: operands live on different devices: %s'
+                       % sorted(str(d) for d in devs))
+    dev = devs.pop() if devs else _device()
+    if dev.type != 'cuda':
+      raise ValueError('ddsp_b200: operands must be CUDA tensors, got %s' % dev)
+    self._ctx = torch.cuda.device(dev)
+
+  def __enter__(self):
+    return self._ctx.__enter__()
+
+  def __exit__(self, *exc):
+    return self._ctx.__exit__(*exc)
+
+
+def _check_out(out, shape, like, name='out'):
+  """`out=` of the synthesizers is written by a kernel: B*N floats at data_ptr."""
+  if (not isinstance(out, torch.Tensor) or not out.is_cuda or
+      out.dtype != torch.float32 or not out.is_contiguous() or
+      tuple(out.shape) != tuple(shape) or out.device != like.device):
+    raise ValueError(
+        f'{name} must be a contiguous float32 CUDA tensor of shape {tuple(shape)} '
+        f'on {like.device}; got {type(out).__name__}'
+        + (f' {tuple(out.shape)} {out.dtype} {out.device}' if isinstance(out, torch.Tensor) else ''))
+
+
+def _no_grad_path(name, *tensors):
+  """The kernels behind `core.*` / Processor / ProcessorGroup do not record an
+  autograd graph.  A training loop that relies on gradients must go through
+  ddsp_b200.autograd (decoder_train / HarmonicSynthesisFn / FilteredNoiseFn);
+  silently returning detached audio would train nothing."""
+  if torch.is_grad_enabled() and any(
+      isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+    raise RuntimeError(
+        f'ddsp_b200.core.{name}: an input requires grad, but this call is the '
+        'inference path and returns detached audio.  Use ddsp_b200.autograd.'
+        'decoder_train / HarmonicSynthesisFn / FilteredNoiseFn (CUDA backward '
+        'kernels), or wrap the call in torch.no_grad().')
+
+
 def _ptr(t):
   return 0 if t is None else t.data_ptr()
 
@@ -109,10 +155,12 @@ def _ptr(t):
 def exp_sigmoid(x, exponent=10.0, max_value=2.0, threshold=1e-7):
   """core.py:386-404.  Default arguments run the CUDA controls kernel."""
   x = torch_float32(x)
-  if (exponent, max_value, threshold) == (10.0, 2.0, 1e-7):
+  if (exponent, max_value, threshold) == (10.0, 2.0, 1e-7) and not (
+      torch.is_grad_enabled() and x.requires_grad):
     out = torch.empty_like(x)
-    _lib.check(_lib.load().ddsp_b200_noise_controls(
-        _ptr(x), _ptr(out), x.numel(), 0.0, 1, _stream()))
+    with _on_device_of(x):
+      _lib.check(_lib.load().ddsp_b200_noise_controls(
+          _ptr(x), _ptr(out), x.numel(), 0.0, 1, _stream()))
     return out
   return max_value * torch.sigmoid(x)**float(np.log(exponent)) + threshold
 
@@ -232,7 +280,7 @@ def frequencies_sigmoid(freqs, depth: int = 1, hz_min: float = 0.0,
 # ----------------------------------------------------------------------------
 # Resampling (core.py:573-714) - stand-alone ops (the synthesizers fuse them)
 # ----------------------------------------------------------------------------
-_RESAMPLE_METHODS = {'window': 0, 'linear': 1, 'nearest': 2}
+_RESAMPLE_METHODS = {'window': 0, 'linear': 1, 'nearest': 2, 'cubic': 3}
 
 
 def _resample_3d(inputs, n_timesteps, method, add_endpoint):
@@ -240,9 +288,10 @@ def _resample_3d(inputs, n_timesteps, method, add_endpoint):
   b, f, c = inputs.shape
   out = torch.empty((b, int(n_timesteps), c), dtype=torch.float32,
                     device=inputs.device)
-  _lib.check(_lib.load().ddsp_b200_resample(
-      _ptr(inputs), _ptr(out), b, f, c, int(n_timesteps),
-      _RESAMPLE_METHODS[method], int(bool(add_endpoint)), _stream()))
+  with _on_device_of(inputs):
+    _lib.check(_lib.load().ddsp_b200_resample(
+        _ptr(inputs), _ptr(out), b, f, c, int(n_timesteps),
+        _RESAMPLE_METHODS[method], int(bool(add_endpoint)), _stream()))
   return out
 
 
@@ -269,20 +318,27 @@ def upsample_with_windows(inputs, n_timesteps: int, add_endpoint: bool = True):
 
 def resample(inputs, n_timesteps: int, method: Text = 'linear',
              add_endpoint: bool = True):
-  """core.resample (core.py:573-642) for 1-D / 2-D / 3-D inputs."""
+  """core.resample (core.py:573-642) for 1-D / 2-D / 3-D / 4-D inputs, methods
+  'nearest', 'linear', 'cubic' (tf.compat.v1 image kernels) and 'window'."""
   shape = _shape(inputs)
   if method not in ('nearest', 'linear', 'cubic', 'window'):
     raise ValueError('Method ({}) is invalid. Must be one of {}.'.format(
         method, "['nearest', 'linear', 'cubic', 'window']"))
-  if method == 'cubic':
-    raise NotImplementedError("'cubic' resampling is not built.")
-  if len(shape) not in (1, 2, 3):
-    raise NotImplementedError('4-D resample is outside the decoder path.')
+  if len(shape) not in (1, 2, 3, 4):
+    raise ValueError(f'resample takes 1-D to 4-D inputs, got shape {list(shape)}.')
   x = torch_float32(inputs)
   if len(shape) == 1:
     x = x[None, :, None]
   elif len(shape) == 2:
     x = x[:, :, None]
+  elif len(shape) == 4:
+    if method == 'window':
+      # upsample_with_windows only takes 3-D (core.py:670-672)
+      raise ValueError('Upsample_with_windows() only supports 3 dimensions, '
+                       'not {}.'.format(list(shape)))
+    # core.py:616-621 resizes [n_frames, n_freq] to [n_timesteps, n_freq]: the
+    # n_freq axis maps onto itself, so this is the 3-D case over n_freq*channels.
+    x = x.reshape(shape[0], shape[1], shape[2] * shape[3])
   if method == 'window':
     out = upsample_with_windows(x, n_timesteps, add_endpoint)
   else:
@@ -291,6 +347,8 @@ def resample(inputs, n_timesteps: int, method: Text = 'linear',
     out = out[0, :, 0]
   elif len(shape) == 2:
     out = out[:, :, 0]
+  elif len(shape) == 4:
+    out = out.reshape(shape[0], int(n_timesteps), shape[2], shape[3])
   return out
 
 
@@ -317,9 +375,11 @@ def harmonic_controls(amplitudes, harmonic_distribution, f0_hz, sample_rate,
   hd_out = torch.empty_like(hd)
   flags = ((_lib.CTL_SCALE if scale else 0) |
            (_lib.CTL_NYQUIST if normalize_below_nyquist else 0))
-  _lib.check(_lib.load().ddsp_b200_harmonic_controls(
-      _ptr(amplitudes), _ptr(hd), _ptr(f0_hz), _ptr(amps_out), _ptr(hd_out),
-      b, f, k, float(sample_rate), flags, _stream()))
+  _no_grad_path('harmonic_controls', amplitudes, hd, f0_hz)
+  with _on_device_of(amplitudes, hd, f0_hz):
+    _lib.check(_lib.load().ddsp_b200_harmonic_controls(
+        _ptr(amplitudes), _ptr(hd), _ptr(f0_hz), _ptr(amps_out), _ptr(hd_out),
+        b, f, k, float(sample_rate), flags, _stream()))
   return amps_out, hd_out
 
 
@@ -363,13 +423,56 @@ def normalize_harmonics(harmonic_distribution, f0_hz=None, sample_rate=None):
   return hd
 
 
+def angular_cumsum(angular_frequency, chunk_size: int = 1000,
+                   tf_sequential: bool = False):
+  """core.angular_cumsum (core.py:799-866): accumulated phase in [0, 2 pi) of an
+  angular frequency [batch, time, ...] in radians per sample.
+
+  Default: the wrapped running sum computed EXACTLY (64-bit fixed-point turns,
+  three-pass scan) - the quantity the reference's chunked float32 cumsum
+  approximates; `chunk_size` does not matter then.  tf_sequential=True reproduces
+  the reference's own float32 arithmetic in its own order (chunks of
+  `chunk_size`, mod-2pi stitching) - a debug mode for comparing against
+  TensorFlow, one thread per (batch, channel)."""
+  x = torch_float32(angular_frequency)
+  shape = tuple(x.shape)
+  if len(shape) < 2:
+    raise ValueError(f'angular_frequency must be [batch, time, ...], got {list(shape)}.')
+  b, n = shape[0], shape[1]
+  c = 1
+  for d in shape[2:]:
+    c *= int(d)
+  x3 = x.reshape(b, n, max(c, 1))
+  out = torch.empty_like(x3)
+  lib = _lib.load()
+  with _on_device_of(x3):
+    if tf_sequential:
+      _lib.check(lib.ddsp_b200_angular_cumsum(
+          _ptr(x3), _ptr(out), b, n, max(c, 1), int(chunk_size), 2, None, 0,
+          _stream()))
+    else:
+      nbytes = lib.ddsp_b200_oscillator_bank_workspace(b, n, max(c, 1))
+      ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x3.device)
+      _lib.check(lib.ddsp_b200_angular_cumsum(
+          _ptr(x3), _ptr(out), b, n, max(c, 1), int(chunk_size), 0, _ptr(ws),
+          nbytes, _stream()))
+  return out.reshape(shape)
+
+
 def oscillator_bank(frequency_envelopes, amplitude_envelopes,
                     sample_rate: int = 16000, sum_sinusoids: bool = True,
-                    use_angular_cumsum: bool = False):
+                    use_angular_cumsum: bool = False,
+                    phase_mode: Text = 'exact'):
   """core.oscillator_bank (core.py:911-962) on audio-rate envelopes
-  [batch, n_samples, n_sinusoids].  Phase is accumulated exactly (wrapped,
-  64-bit fixed point) whatever `use_angular_cumsum` says."""
-  del use_angular_cumsum
+  [batch, n_samples, n_sinusoids].
+
+  phase_mode='exact' (default): phase is accumulated wrapped and exactly (64-bit
+  fixed point) whatever `use_angular_cumsum` says - both reference modes
+  approximate this.  phase_mode='tf_sequential': the reference's own float32
+  arithmetic in its own order - tf.cumsum, or angular_cumsum (chunks of 1000)
+  when use_angular_cumsum - reproducing TensorFlow's phase error (debug)."""
+  if phase_mode not in ('exact', 'tf_sequential'):
+    raise ValueError(f"phase_mode must be 'exact' or 'tf_sequential', got {phase_mode!r}.")
   sf, sa = _shape(frequency_envelopes), _shape(amplitude_envelopes)
   if len(sf) != 3 or sf != sa:
     raise ValueError(f'frequency_envelopes {sf} and amplitude_envelopes {sa} must '
@@ -377,14 +480,55 @@ def oscillator_bank(frequency_envelopes, amplitude_envelopes,
   b, n, k = sf
   f = torch_float32(frequency_envelopes)
   a = torch_float32(amplitude_envelopes)
+  _no_grad_path('oscillator_bank', f, a)
   lib = _lib.load()
-  out = torch.empty((b, n) if sum_sinusoids else (b, n, k), dtype=torch.float32,
-                    device=f.device)
-  nbytes = lib.ddsp_b200_oscillator_bank_workspace(b, n, k)
-  ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=f.device)
-  _lib.check(lib.ddsp_b200_oscillator_bank(
-      _ptr(f), _ptr(a), _ptr(out), b, n, k, float(sample_rate),
-      int(bool(sum_sinusoids)), _ptr(ws), nbytes, _stream()))
+  with _on_device_of(f, a):
+    if phase_mode == 'tf_sequential':
+      wavs = torch.empty((b, n, k), dtype=torch.float32, device=f.device)
+      _lib.check(lib.ddsp_b200_oscillator_bank_tf_sequential(
+          _ptr(f), _ptr(a), _ptr(wavs), b, n, k, float(sample_rate),
+          int(bool(use_angular_cumsum)), 1000, _stream()))
+      return wavs.sum(-1) if sum_sinusoids else wavs
+    out = torch.empty((b, n) if sum_sinusoids else (b, n, k), dtype=torch.float32,
+                      device=f.device)
+    nbytes = lib.ddsp_b200_oscillator_bank_workspace(b, n, k)
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=f.device)
+    _lib.check(lib.ddsp_b200_oscillator_bank(
+        _ptr(f), _ptr(a), _ptr(out), b, n, k, float(sample_rate),
+        int(bool(sum_sinusoids)), _ptr(ws), nbytes, _stream()))
+  return out
+
+
+def sinusoidal_synthesis(frequencies, amplitudes, n_samples: int = 64000,
+                         sample_rate: int = 16000,
+                         amp_resample_method: Text = 'window', out=None,
+                         accumulate: bool = False):
+  """Frame-rate bank of sinusoids with per-sinusoid frequencies
+  [batch, n_frames, n_sinusoids] -> audio [batch, n_samples]: the fused form of
+  resample + resample + core.oscillator_bank (synths.py:305-323) - the
+  [batch, n_samples, n_sinusoids] envelopes are never materialised."""
+  sf, sa = _shape(frequencies), _shape(amplitudes)
+  if len(sf) != 3 or sf != sa:
+    raise ValueError(f'frequencies {sf} and amplitudes {sa} must both be '
+                     '[batch, n_frames, n_sinusoids].')
+  b, f, k = sf
+  n_samples = int(n_samples)
+  freqs = torch_float32(frequencies)
+  amps = torch_float32(amplitudes)
+  _no_grad_path('sinusoidal_synthesis', freqs, amps)
+  if out is None:
+    out = torch.empty((b, n_samples), dtype=torch.float32, device=freqs.device)
+    accumulate = False
+  else:
+    _check_out(out, (b, n_samples), freqs)
+  lib = _lib.load()
+  with _on_device_of(freqs, amps, out):
+    nbytes = lib.ddsp_b200_sinusoidal_workspace(b, f, k)
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=freqs.device)
+    _lib.check(lib.ddsp_b200_sinusoidal_forward(
+        _ptr(freqs), _ptr(amps), _ptr(out), b, f, k, n_samples, float(sample_rate),
+        AMP_METHODS[amp_resample_method], int(bool(accumulate)), _ptr(ws), nbytes,
+        _stream()))
   return out
 
 
@@ -399,25 +543,32 @@ def harmonic_synthesis(frequencies,
                        out: Optional[torch.Tensor] = None,
                        accumulate: bool = False,
                        phase_mode: Text = 'recurrence'):
-  """core.harmonic_synthesis (core.py:1048-1111) as one fused kernel.
+  """core.harmonic_synthesis (core.py:1048-1111).
 
-  `use_angular_cumsum` is accepted for API parity; phase is always accumulated
-  wrapped and exactly (64-bit fixed point), which is what angular_cumsum
-  approximates (core.py:803-817) - see DESIGN.md "phase".
+  The common case (no harmonic_shifts, 'window' / 'linear' amplitudes, n_samples
+  a multiple of the frame count) is ONE fused kernel.  With `harmonic_shifts`
+  (core.py:1084-1093) the harmonics are no longer integer multiples of one
+  phase: f0 * k * (1 + shift) and amp * hd are formed at frame rate, as the
+  reference does, and the frame-rate oscillator bank with per-sinusoid phases
+  (`sinusoidal_synthesis`) takes over.  'nearest' / 'cubic' amplitudes and
+  non-integer hops take the reference's own decomposition on our kernels:
+  `resample` + `resample` + `oscillator_bank` (audio-rate envelopes exist then).
+
+  Phase is accumulated wrapped and exactly (64-bit fixed point) whatever
+  `use_angular_cumsum` says - that is what angular_cumsum approximates
+  (core.py:803-817; DESIGN.md "phase").  phase_mode: 'recurrence' (default) /
+  'direct' choose how sin(k phi) is evaluated in the fused kernel;
+  'tf_sequential' reproduces TensorFlow's float32 phase arithmetic in its own
+  order (tf.cumsum, or angular_cumsum if use_angular_cumsum) - a debug mode for
+  small shapes that materialises the envelopes.
   """
-  del use_angular_cumsum
-  if harmonic_shifts is not None:
-    raise NotImplementedError(
-        'harmonic_shifts is outside the Harmonic processor path '
-        '(synths.py:138-146 never passes it).')
   if amp_resample_method not in ('nearest', 'linear', 'cubic', 'window'):
     # core.py:632-634
     raise ValueError('Method ({}) is invalid. Must be one of {}.'.format(
         amp_resample_method, "['nearest', 'linear', 'cubic', 'window']"))
-  if amp_resample_method not in AMP_METHODS:
-    raise NotImplementedError(
-        f"amp_resample_method='{amp_resample_method}' is not built; "
-        "'window' and 'linear' are.")
+  if phase_mode not in ('recurrence', 'direct', 'tf_sequential'):
+    raise ValueError("phase_mode must be 'recurrence', 'direct' or "
+                     f"'tf_sequential', got {phase_mode!r}.")
   sf, sa = _shape(frequencies), _shape(amplitudes)
   if len(sf) != 3 or len(sa) != 3:
     # core.py:670-672 (the window upsampler only takes 3-D inputs)
@@ -434,6 +585,13 @@ def harmonic_synthesis(frequencies,
       raise ValueError(f'harmonic_distribution {sh} must be [{b}, {f}, '
                        'n_harmonics].')
     k = int(sh[-1])
+  if harmonic_shifts is not None:
+    ss = _shape(harmonic_shifts)
+    if len(ss) != 3 or ss[:2] != (b, f) or (harmonic_distribution is not None
+                                             and ss[-1] != k):
+      raise ValueError(f'harmonic_shifts {ss} must be [{b}, {f}, n_harmonics'
+                       f'{"=" + str(k) if harmonic_distribution is not None else ""}].')
+    k = int(ss[-1])
   n_samples = int(n_samples)
   if amp_resample_method == 'window':
     if f >= n_samples:
@@ -447,24 +605,62 @@ def harmonic_synthesis(frequencies,
           'For upsampling, the target the number of timesteps must be divisible '
           'by the number of input frames{}. (timesteps:{}, frames:{}, '
           'add_endpoint={}).'.format('', n_samples, f + 1, True))
-  if n_samples % f != 0:
-    raise NotImplementedError(
-        f'n_samples ({n_samples}) must be a multiple of the number of frames '
-        f'({f}): non-integer hops are not built.')
-  mode = {'recurrence': _lib.PHASE_RECURRENCE, 'direct': _lib.PHASE_DIRECT}[
-      phase_mode]
   frequencies = torch_float32(frequencies)
   amplitudes = torch_float32(amplitudes)
   if harmonic_distribution is not None:
     harmonic_distribution = torch_float32(harmonic_distribution)
-  if out is None:
-    out = torch.empty((b, n_samples), dtype=torch.float32,
-                      device=frequencies.device)
+  if harmonic_shifts is not None:
+    harmonic_shifts = torch_float32(harmonic_shifts)
+  _no_grad_path('harmonic_synthesis', frequencies, amplitudes, harmonic_distribution,
+                harmonic_shifts)
+  if out is not None:
+    _check_out(out, (b, n_samples), frequencies)
+  else:
     accumulate = False
-  _lib.check(_lib.load().ddsp_b200_harmonic_forward(
-      _ptr(frequencies), _ptr(amplitudes), _ptr(harmonic_distribution),
-      _ptr(out), b, f, k, n_samples, float(sample_rate),
-      AMP_METHODS[amp_resample_method], mode, int(bool(accumulate)), _stream()))
+
+  fused_ok = (amp_resample_method in AMP_METHODS and n_samples % f == 0 and
+              phase_mode != 'tf_sequential')
+  if harmonic_shifts is None and fused_ok:
+    mode = {'recurrence': _lib.PHASE_RECURRENCE, 'direct': _lib.PHASE_DIRECT}[
+        phase_mode]
+    if out is None:
+      out = torch.empty((b, n_samples), dtype=torch.float32,
+                        device=frequencies.device)
+    with _on_device_of(frequencies, amplitudes, harmonic_distribution, out):
+      _lib.check(_lib.load().ddsp_b200_harmonic_forward(
+          _ptr(frequencies), _ptr(amplitudes), _ptr(harmonic_distribution),
+          _ptr(out), b, f, k, n_samples, float(sample_rate),
+          AMP_METHODS[amp_resample_method], mode, int(bool(accumulate)), _stream()))
+    return out
+
+  # frame-rate harmonic frequencies / amplitudes, float32 op for op as the
+  # reference (core.py:1091-1099): (f0 * k) * (1 + shifts), amplitudes * hd
+  with _on_device_of(frequencies, amplitudes, harmonic_distribution, harmonic_shifts):
+    harmonic_frequencies = get_harmonic_frequencies(frequencies, k)
+    if harmonic_shifts is not None:
+      harmonic_frequencies = harmonic_frequencies * (1.0 + harmonic_shifts)
+    harmonic_amplitudes = (amplitudes * harmonic_distribution
+                           if harmonic_distribution is not None
+                           else amplitudes.expand(b, f, k).contiguous())
+    if fused_ok:
+      return sinusoidal_synthesis(harmonic_frequencies, harmonic_amplitudes,
+                                  n_samples=n_samples, sample_rate=sample_rate,
+                                  amp_resample_method=amp_resample_method, out=out,
+                                  accumulate=accumulate)
+    # core.py:1101-1110 on the stand-alone kernels (audio-rate envelopes exist)
+    frequency_envelopes = resample(harmonic_frequencies, n_samples)
+    amplitude_envelopes = resample(harmonic_amplitudes, n_samples,
+                                   method=amp_resample_method)
+    audio = oscillator_bank(
+        frequency_envelopes, amplitude_envelopes, sample_rate=sample_rate,
+        use_angular_cumsum=use_angular_cumsum,
+        phase_mode='tf_sequential' if phase_mode == 'tf_sequential' else 'exact')
+  if out is None:
+    return audio
+  if accumulate:
+    out += audio
+  else:
+    out.copy_(audio)
   return out
 
 
@@ -642,6 +838,7 @@ def fft_convolve(audio, impulse_response, padding: Text = 'same',
                               fft_size, int(start), int(crop_size))
     if out is None:
       return wet
+    _check_out(out, tuple(wet.shape), audio)
     if accumulate:
       out += wet
     else:
@@ -651,11 +848,16 @@ def fft_convolve(audio, impulse_response, padding: Text = 'same',
     out = torch.empty((batch_size, crop_size), dtype=torch.float32,
                       device=audio.device)
     accumulate = False
-  _lib.check(_lib.load().ddsp_b200_fir_time_varying(
-      _ptr(audio), _ptr(impulse_response.contiguous()), _ptr(out), batch_size,
-      audio_size, n_ir_frames, ir_size, ir_batch,
-      _lib.PAD_SAME if padding == 'same' else _lib.PAD_VALID,
-      int(start), int(bool(accumulate)), _stream()))
+  else:
+    _check_out(out, (batch_size, crop_size), audio)
+  impulse_response = impulse_response.contiguous()
+  _no_grad_path('fft_convolve', audio, impulse_response)
+  with _on_device_of(audio, impulse_response, out):
+    _lib.check(_lib.load().ddsp_b200_fir_time_varying(
+        _ptr(audio), _ptr(impulse_response), _ptr(out), batch_size,
+        audio_size, n_ir_frames, ir_size, ir_batch,
+        _lib.PAD_SAME if padding == 'same' else _lib.PAD_VALID,
+        int(start), int(bool(accumulate)), _stream()))
   return out
 
 
@@ -707,15 +909,19 @@ def filtered_noise(magnitudes, n_samples, window_size=257, noise=None, seed=0,
     out = torch.empty((b, n_samples), dtype=torch.float32,
                       device=magnitudes.device)
     accumulate = False
-  ws_bytes = lib.ddsp_b200_filtered_noise_workspace(b, f, nb, n_samples,
-                                                    int(window_size))
-  workspace = (torch.empty((ws_bytes,), dtype=torch.uint8,
-                           device=magnitudes.device) if ws_bytes else None)
-  _lib.check(lib.ddsp_b200_filtered_noise_forward(
-      _ptr(magnitudes), _ptr(noise), int(seed) & (2**64 - 1),
-      int(offset) & (2**64 - 1), _ptr(out), b, f, nb, n_samples,
-      int(window_size), int(bool(accumulate)), _ptr(workspace), ws_bytes,
-      _stream()))
+  else:
+    _check_out(out, (b, n_samples), magnitudes)
+  _no_grad_path('filtered_noise', magnitudes)
+  with _on_device_of(magnitudes, noise, out):
+    ws_bytes = lib.ddsp_b200_filtered_noise_workspace(b, f, nb, n_samples,
+                                                      int(window_size))
+    workspace = (torch.empty((ws_bytes,), dtype=torch.uint8,
+                             device=magnitudes.device) if ws_bytes else None)
+    _lib.check(lib.ddsp_b200_filtered_noise_forward(
+        _ptr(magnitudes), _ptr(noise), int(seed) & (2**64 - 1),
+        int(offset) & (2**64 - 1), _ptr(out), b, f, nb, n_samples,
+        int(window_size), int(bool(accumulate)), _ptr(workspace), ws_bytes,
+        _stream()))
   return out
 
 
@@ -748,23 +954,27 @@ def decoder_forward(amps, harmonic_distribution, f0_hz, noise_magnitudes,
   mags = torch_float32(noise_magnitudes)
   if noise is not None:
     noise = torch_float32(noise)
+  _no_grad_path('decoder_forward', amps, hd, f0_hz, mags)
   out = torch.empty((b, n_samples), dtype=torch.float32, device=hd.device)
   flags = _lib.CTL_SCALE | (_lib.CTL_NYQUIST if normalize_below_nyquist else 0)
-  _lib.check(_lib.load().ddsp_b200_decoder_forward(
-      _ptr(amps), _ptr(hd), _ptr(f0_hz), _ptr(mags), _ptr(noise),
-      int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _ptr(out), b, f, k,
-      sm[2], n_samples, float(sample_rate), AMP_METHODS[amp_resample_method],
-      flags, int(window_size), float(initial_bias), _stream()))
+  with _on_device_of(amps, hd, f0_hz, mags, noise):
+    _lib.check(_lib.load().ddsp_b200_decoder_forward(
+        _ptr(amps), _ptr(hd), _ptr(f0_hz), _ptr(mags), _ptr(noise),
+        int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), _ptr(out), b, f, k,
+        sm[2], n_samples, float(sample_rate), AMP_METHODS[amp_resample_method],
+        flags, int(window_size), float(initial_bias), _stream()))
   return out
 
 
 def noise_controls(magnitudes, initial_bias=-5.0, scale=True):
   """FilteredNoise.get_controls arithmetic (synths.py:165-179)."""
   magnitudes = torch_float32(magnitudes)
+  _no_grad_path('noise_controls', magnitudes)
   out = torch.empty_like(magnitudes)
-  _lib.check(_lib.load().ddsp_b200_noise_controls(
-      _ptr(magnitudes), _ptr(out), magnitudes.numel(), float(initial_bias),
-      int(bool(scale)), _stream()))
+  with _on_device_of(magnitudes):
+    _lib.check(_lib.load().ddsp_b200_noise_controls(
+        _ptr(magnitudes), _ptr(out), magnitudes.numel(), float(initial_bias),
+        int(bool(scale)), _stream()))
   return out
 
 

@@ -17,6 +17,7 @@
 #include "host_pipeline.cuh"
 #include "backward.cuh"
 #include "oscbank.cuh"
+#include "sinusoidal.cuh"
 #include "spectral.cuh"
 
 namespace ddsp {
@@ -631,8 +632,8 @@ int ddsp_b200_harmonic_backward(const float* f0_hz, const float* grad_audio,
                "harmonic_backward: needs hop %% 64 == 0 (hop = %d)", p.hop);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t gbytes = sizeof(float) * (size_t)B * F * K;
-  cudaMemsetAsync(g0, 0, gbytes, st);
-  cudaMemsetAsync(g1, 0, gbytes, st);
+  DDSP_CUDA_TRY(cudaMemsetAsync(g0, 0, gbytes, st), "harmonic_backward: memset g0");
+  DDSP_CUDA_TRY(cudaMemsetAsync(g1, 0, gbytes, st), "harmonic_backward: memset g1");
   p.FT = std::max(1, std::min(F, 2048 / p.hop));
   const size_t smem = harmonic_backward_smem(p.FT, p.hop);
   dim3 grid((F + p.FT - 1) / p.FT, B);
@@ -741,12 +742,148 @@ int ddsp_b200_oscillator_bank(const float* frequency_envelopes,
   return 0;
 }
 
+int ddsp_b200_angular_cumsum(const float* angular_frequency, float* phase, int B,
+                             int N, int C, int chunk_size, int mode,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  DDSP_REQUIRE(angular_frequency && phase, DDSP_B200_E_INVALID,
+               "angular_cumsum: null pointer");
+  DDSP_REQUIRE(B >= 0 && N >= 1 && C >= 1, DDSP_B200_E_INVALID,
+               "angular_cumsum: bad shape B=%d N=%d C=%d", B, N, C);
+  DDSP_REQUIRE(mode >= 0 && mode <= 2, DDSP_B200_E_INVALID,
+               "angular_cumsum: bad mode %d", mode);
+  DDSP_REQUIRE(mode != 2 || chunk_size >= 1, DDSP_B200_E_INVALID,
+               "angular_cumsum: chunk_size must be positive");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode != 0) {
+    const int64_t BC = (int64_t)B * C;
+    tf_sequential_cumsum<<<(int)((BC + 127) / 128), 128, 0, st>>>(
+        angular_frequency, nullptr, phase, B, N, C, mode, chunk_size, 0, 1.0f);
+    DDSP_CHECK_LAUNCH("angular_cumsum(tf_sequential)");
+    return 0;
+  }
+  DDSP_REQUIRE(B <= 65535, DDSP_B200_E_INVALID,
+               "angular_cumsum: B=%d exceeds the 65535 grid limit", B);
+  const size_t need = ddsp_b200_oscillator_bank_workspace(B, N, C);
+  DDSP_REQUIRE(workspace != nullptr && workspace_bytes >= need, DDSP_B200_E_WORKSPACE,
+               "angular_cumsum: workspace of %zu B needed, %zu given", need,
+               workspace_bytes);
+  unsigned long long* sums = reinterpret_cast<unsigned long long*>(
+      ((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const int n_chunks = (N + kObChunk - 1) / kObChunk;
+  const double inv_two_pi = 0.15915494309189535;
+  dim3 grid(n_chunks, B);
+  oscbank_chunk_sums<<<grid, kObThreads, 0, st>>>(angular_frequency, sums, N, C,
+                                                 n_chunks, inv_two_pi);
+  DDSP_CHECK_LAUNCH("angular_cumsum(chunk sums)");
+  const int64_t BK = (int64_t)B * C;
+  oscbank_scan_chunks<<<(int)((BK + kObThreads - 1) / kObThreads), kObThreads, 0, st>>>(
+      sums, C, n_chunks, BK);
+  DDSP_CHECK_LAUNCH("angular_cumsum(scan)");
+  oscbank_phase_out<<<grid, kObThreads, 0, st>>>(angular_frequency, sums, phase, N, C,
+                                                n_chunks, inv_two_pi);
+  DDSP_CHECK_LAUNCH("angular_cumsum(apply)");
+  return 0;
+}
+
+int ddsp_b200_oscillator_bank_tf_sequential(const float* frequency_envelopes,
+                                            const float* amplitude_envelopes,
+                                            float* out, int B, int N, int K,
+                                            float sample_rate, int use_angular_cumsum,
+                                            int chunk_size, void* stream) {
+  DDSP_REQUIRE(frequency_envelopes && amplitude_envelopes && out, DDSP_B200_E_INVALID,
+               "oscillator_bank_tf_sequential: null pointer");
+  DDSP_REQUIRE(B >= 0 && N >= 1 && K >= 1 && chunk_size >= 1 && sample_rate > 0.f,
+               DDSP_B200_E_INVALID, "oscillator_bank_tf_sequential: bad arguments");
+  if (B == 0) return 0;
+  const int64_t BK = (int64_t)B * K;
+  tf_sequential_cumsum<<<(int)((BK + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      frequency_envelopes, amplitude_envelopes, out, B, N, K,
+      use_angular_cumsum ? 2 : 1, chunk_size, 1, sample_rate);
+  DDSP_CHECK_LAUNCH("oscillator_bank_tf_sequential");
+  return 0;
+}
+
+static int sinus_tile_frames(int F, int K) {
+  int FT = std::min(16, F);
+  while (FT > 1 && sf_smem(FT, K).total > kMaxDynSmem) FT = (FT + 1) / 2;
+  return FT;
+}
+
+size_t ddsp_b200_sinusoidal_workspace(int B, int F, int K) {
+  if (B <= 0 || F <= 0 || K <= 0) return 0;
+  const int FT = sinus_tile_frames(F, K);
+  const size_t n_tiles = ((size_t)F + FT - 1) / FT;
+  return sizeof(unsigned long long) * (size_t)B * n_tiles * K + 256;
+}
+
+int ddsp_b200_sinusoidal_forward(const float* frequencies, const float* amplitudes,
+                                 float* audio, int B, int F, int K, int N,
+                                 float sample_rate, int amp_method, int accumulate,
+                                 void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  DDSP_REQUIRE(frequencies && amplitudes && audio, DDSP_B200_E_INVALID,
+               "sinusoidal_forward: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && K >= 1 && N >= 1, DDSP_B200_E_INVALID,
+               "sinusoidal_forward: bad shape B=%d F=%d K=%d N=%d", B, F, K, N);
+  DDSP_REQUIRE(amp_method == DDSP_B200_AMP_WINDOW || amp_method == DDSP_B200_AMP_LINEAR,
+               DDSP_B200_E_INVALID, "sinusoidal_forward: bad amp_method %d", amp_method);
+  DDSP_REQUIRE(N % F == 0, DDSP_B200_E_INVALID,
+               "sinusoidal_forward: n_samples (%d) must be divisible by the number "
+               "of frames (%d)", N, F);
+  DDSP_REQUIRE(amp_method != DDSP_B200_AMP_WINDOW || F < N, DDSP_B200_E_INVALID,
+               "sinusoidal_forward: window upsampling cannot downsample (frames %d "
+               ">= timesteps %d)", F, N);
+  DDSP_REQUIRE(sample_rate > 0.f, DDSP_B200_E_INVALID,
+               "sinusoidal_forward: sample_rate must be positive");
+  if (B == 0) return 0;
+  DDSP_REQUIRE(B <= 65535, DDSP_B200_E_INVALID,
+               "sinusoidal_forward: B=%d exceeds the 65535 grid limit", B);
+  const int FT = sinus_tile_frames(F, K);
+  const SfSmem L = sf_smem(FT, K);
+  DDSP_REQUIRE(L.total <= kMaxDynSmem, DDSP_B200_E_UNSUPPORTED,
+               "sinusoidal_forward: K=%d needs more shared memory than one CTA has", K);
+  const size_t need = ddsp_b200_sinusoidal_workspace(B, F, K);
+  DDSP_REQUIRE(workspace != nullptr && workspace_bytes >= need, DDSP_B200_E_WORKSPACE,
+               "sinusoidal_forward: workspace of %zu B needed, %zu given", need,
+               workspace_bytes);
+  unsigned long long* sums = reinterpret_cast<unsigned long long*>(
+      ((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const int n_tiles = (F + FT - 1) / FT;
+  const int hop = N / F;
+  const double inv_sr = 1.0 / (double)sample_rate;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(n_tiles, B);
+  sinus_tile_sums<<<grid, kSfThreads, 0, st>>>(frequencies, sums, F, K, hop, FT, n_tiles,
+                                              inv_sr);
+  DDSP_CHECK_LAUNCH("sinusoidal_forward(tile sums)");
+  const int64_t BK = (int64_t)B * K;
+  oscbank_scan_chunks<<<(int)((BK + kObThreads - 1) / kObThreads), kObThreads, 0, st>>>(
+      sums, K, n_tiles, BK);
+  DDSP_CHECK_LAUNCH("sinusoidal_forward(scan)");
+  if (amp_method == DDSP_B200_AMP_WINDOW) {
+    int rc = set_smem(sinus_apply<true>, L.total, "sinusoidal_forward");
+    if (rc) return rc;
+    sinus_apply<true><<<grid, kSfThreads, L.total, st>>>(
+        frequencies, amplitudes, sums, audio, F, K, N, hop, FT, n_tiles, inv_sr,
+        sample_rate * 0.5f, accumulate);
+  } else {
+    int rc = set_smem(sinus_apply<false>, L.total, "sinusoidal_forward");
+    if (rc) return rc;
+    sinus_apply<false><<<grid, kSfThreads, L.total, st>>>(
+        frequencies, amplitudes, sums, audio, F, K, N, hop, FT, n_tiles, inv_sr,
+        sample_rate * 0.5f, accumulate);
+  }
+  DDSP_CHECK_LAUNCH("sinusoidal_forward(apply)");
+  return 0;
+}
+
 int ddsp_b200_resample(const float* in, float* out, int B, int F, int C, int N,
                        int method, int add_endpoint, void* stream) {
   DDSP_REQUIRE(in && out, DDSP_B200_E_INVALID, "resample: null pointer");
   DDSP_REQUIRE(B >= 0 && F >= 1 && C >= 1 && N >= 1, DDSP_B200_E_INVALID,
                "resample: bad shape B=%d F=%d C=%d N=%d", B, F, C, N);
-  DDSP_REQUIRE(method >= 0 && method <= 2, DDSP_B200_E_INVALID,
+  DDSP_REQUIRE(method >= 0 && method <= 3, DDSP_B200_E_INVALID,
                "resample: bad method %d", method);
   if (method == 0) {
     // upsample_with_windows (core.py:676-693)

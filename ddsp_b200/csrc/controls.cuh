@@ -63,7 +63,7 @@ add_kernel(const float* a, const float* b, float* out, int64_t n) {
 // core.resample / core.upsample_with_windows (core.py:573-714) as a stand-alone
 // op: [B, F, C] -> [B, N, C].  method 0 = 'window' (Hann overlap-add ==
 // two-tap raised cosine), 1 = 'linear' (tf v1 bilinear,
-// align_corners = !add_endpoint), 2 = 'nearest'.  Index math follows TF's
+// align_corners = !add_endpoint), 2 = 'nearest', 3 = 'cubic' (tf v1 bicubic).  Index math follows TF's
 // float32 scale * index for linear / nearest; the window method needs an integer
 // hop (checked by the caller, core.py:687-693).
 __global__ void __launch_bounds__(256)
@@ -94,10 +94,32 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, int B, in
       const int hi = min((int)ceilf(src), F - 1);
       const float top = x[(size_t)min(lo, F - 1) * C], bot = x[(size_t)hi * C];
       v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), src - fl));
-    } else {
+    } else if (method == 2) {
       const float src = (float)t * scale;
       const int i = min((int)(add_endpoint ? floorf(src) : roundf(src)), F - 1);
       v = x[(size_t)i * C];
+    } else {
+      // 'cubic': TensorFlow's legacy bicubic kernel (resize_bicubic_op.cc, Keys
+      // A = -0.75, no half-pixel centres).  Its weights come from a 1025-entry
+      // float32 table indexed by lrintf(delta * 1024); the same entries are
+      // evaluated here in double and rounded to float32.
+      const float src = (float)t * scale;
+      const float fl = floorf(src);
+      const int loc = (int)fl;
+      const int off = (int)lrintf((src - fl) * 1024.0f);
+      const double A = -0.75;
+      const double xa = off * (1.0 / 1024.0), xb = (1024 - off) * (1.0 / 1024.0);
+      const float w1 = (float)(((A + 2) * xa - (A + 3)) * xa * xa + 1);
+      const float w2 = (float)(((A + 2) * xb - (A + 3)) * xb * xb + 1);
+      const double ya = xa + 1.0, yb = xb + 1.0;
+      const float w0 = (float)(((A * ya - 5 * A) * ya + 8 * A) * ya - 4 * A);
+      const float w3 = (float)(((A * yb - 5 * A) * yb + 8 * A) * yb - 4 * A);
+      const float v0 = x[(size_t)min(max(loc - 1, 0), F - 1) * C];
+      const float v1 = x[(size_t)min(max(loc, 0), F - 1) * C];
+      const float v2 = x[(size_t)min(max(loc + 1, 0), F - 1) * C];
+      const float v3 = x[(size_t)min(max(loc + 2, 0), F - 1) * C];
+      v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v0, w0), __fmul_rn(v1, w1)),
+                              __fmul_rn(v2, w2)), __fmul_rn(v3, w3));
     }
     out[idx] = v;
   }

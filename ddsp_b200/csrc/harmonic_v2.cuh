@@ -478,7 +478,13 @@ inline int launch_harmonic_v2(HarmonicParams p, cudaStream_t st) {
     e = win ? launch_one<true, 0>(p, use_tma, FW, grid, smem, st)
             : launch_one<false, 0>(p, use_tma, FW, grid, smem, st);
   }
-  if (e != cudaSuccess) return 1;
+  if (e != cudaSuccess) {
+    // a real error (attribute / launch configuration): report it - falling back to
+    // the generic kernel here would hide a 10x slowdown behind a correct result
+    (void)cudaGetLastError();
+    set_error("harmonic_forward(v2): %s", cudaGetErrorString(e));
+    return DDSP_B200_E_CUDA;
+  }
   DDSP_CHECK_LAUNCH("harmonic_forward(v2)");
   return 0;
 }

@@ -113,11 +113,10 @@ class FilteredNoise(processors.Processor):
 class Sinusoidal(processors.Processor):
   """Bank of arbitrary sinusoidal oscillators (synths.py:260-323).
 
-  get_controls is frame-rate torch arithmetic; get_signal resamples both
-  controls to audio rate (`ddsp_b200_resample`) and runs `ddsp_b200_oscillator_bank`
-  (exact wrapped phase, three-pass chunked scan) - the [batch, n_samples,
-  n_sinusoids] envelopes are materialised here, as in the reference: this
-  processor is outside the fused decoder path."""
+  get_controls is frame-rate torch arithmetic; get_signal is one fused frame-rate
+  oscillator bank with per-sinusoid exact phases
+  (`ddsp_b200_sinusoidal_forward`) - the [batch, n_samples, n_sinusoids]
+  envelopes of the reference are never materialised."""
 
   def __init__(self,
                n_samples=64000,
@@ -146,7 +145,17 @@ class Sinusoidal(processors.Processor):
     return {'amplitudes': amplitudes, 'frequencies': frequencies}
 
   def get_signal(self, amplitudes, frequencies):
-    """synths.py:305-323."""
+    """synths.py:305-323.  One fused frame-rate kernel when the hop is an integer
+    and the amplitudes are resampled by 'window' / 'linear'; otherwise the
+    reference's own decomposition on the stand-alone kernels."""
+    sa = core._shape(amplitudes)  # pylint: disable=protected-access
+    if (self.amp_resample_method in core.AMP_METHODS and len(sa) == 3 and
+        sa[1] > 0 and self.n_samples % sa[1] == 0 and
+        (self.amp_resample_method != 'window' or sa[1] < self.n_samples)):
+      return core.sinusoidal_synthesis(
+          frequencies, amplitudes, n_samples=self.n_samples,
+          sample_rate=self.sample_rate,
+          amp_resample_method=self.amp_resample_method)
     amplitude_envelopes = core.resample(amplitudes, self.n_samples,
                                         method=self.amp_resample_method)
     frequency_envelopes = core.resample(frequencies, self.n_samples)

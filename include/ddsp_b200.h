@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DDSP_B200_VERSION 100 /* 0.1.0 */
+#define DDSP_B200_VERSION 200 /* 0.2.0 */
 
 enum {
   DDSP_B200_OK = 0,
@@ -225,9 +225,46 @@ int ddsp_b200_oscillator_bank(const float* frequency_envelopes,
                               void* workspace, size_t workspace_bytes,
                               void* stream);
 
+/* core.angular_cumsum (core.py:799-866) and tf.cumsum (core.py:955) on
+ * [B,N,C] float32 (C = product of the trailing axes).  mode:
+ *   0  exact: the wrapped running sum in 64-bit fixed point (what angular_cumsum
+ *      approximates), radians in [0, 2 pi); three-pass scan, workspace =
+ *      ddsp_b200_oscillator_bank_workspace(B,N,C) bytes;
+ *   1  tf_sequential, tf.cumsum: float32 running sum in the reference's order;
+ *   2  tf_sequential, angular_cumsum: float32, chunked by chunk_size with the
+ *      reference's mod-2pi stitching (debug mode: reproduces TensorFlow's own
+ *      float32 error, one thread per (b, c) - small shapes).
+ * ddsp_b200_oscillator_bank_tf_sequential is core.oscillator_bank evaluated that
+ * way end to end (omega = f * 2pi / sr in float32, modes 1 / 2, Nyquist mask,
+ * amp * sin(phase)); out is [B,N,K], the sum over k is left to the caller. */
+int ddsp_b200_angular_cumsum(const float* angular_frequency, float* phase, int B,
+                             int N, int C, int chunk_size, int mode,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int ddsp_b200_oscillator_bank_tf_sequential(const float* frequency_envelopes,
+                                            const float* amplitude_envelopes,
+                                            float* out, int B, int N, int K,
+                                            float sample_rate, int use_angular_cumsum,
+                                            int chunk_size, void* stream);
+
+/* Frame-rate oscillator bank with per-sinusoid frequencies: the fusion of
+ * resample(frequencies) + resample(amplitudes, amp_method) + oscillator_bank
+ * for synths.Sinusoidal.get_signal (synths.py:305-323) and for
+ * core.harmonic_synthesis with harmonic_shifts (core.py:1084-1111; the caller
+ * forms f0 * k * (1 + shifts) and amp * hd at frame rate, as the reference does).
+ * frequencies, amplitudes [B,F,K] -> audio [B,N] (summed over k), N % F == 0.
+ * workspace: ddsp_b200_sinusoidal_workspace(B,F,K) bytes. */
+size_t ddsp_b200_sinusoidal_workspace(int B, int F, int K);
+int ddsp_b200_sinusoidal_forward(const float* frequencies, const float* amplitudes,
+                                 float* audio, int B, int F, int K, int N,
+                                 float sample_rate, int amp_method, int accumulate,
+                                 void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
 /* core.resample / core.upsample_with_windows (core.py:573-714) stand-alone:
- * in [B,F,C] -> out [B,N,C].  method: 0 'window', 1 'linear', 2 'nearest'
- * ('cubic' is not built).  add_endpoint as in the reference. */
+ * in [B,F,C] -> out [B,N,C].  method: 0 'window', 1 'linear', 2 'nearest',
+ * 3 'cubic' (tf.compat.v1 bicubic, Keys A = -0.75).  add_endpoint as in the
+ * reference.  4-D inputs [B,F,n_freq,C] are the 3-D case with n_freq*C channels
+ * (the reference resizes the n_freq axis to itself, core.py:616-621). */
 int ddsp_b200_resample(const float* in, float* out, int B, int F, int C, int N,
                        int method, int add_endpoint, void* stream);
 

@@ -162,3 +162,98 @@ def test_in_kernel_noise_statistics():
   # neighbouring samples and neighbouring items are uncorrelated
   assert abs(np.mean(x[:, 1:] * x[:, :-1])) < 3e-3
   assert abs(np.mean(x[0] * x[1])) < 5e-3
+
+
+# ---- configs[2] / configs[3] at their real batch sizes ------------------------
+def test_c3_batch256_spot_check_against_oracle():
+  """BASELINE.json configs[2] (= one GPU's share of configs[4]): B=256 from raw
+  network outputs through the fused ProcessorGroup route; items 0, 101 and 255
+  against the float64 arbiter (which tests/test_reference_pin.py pins to the
+  reference at exactly this item shape)."""
+  B3 = 256
+  inp = synth_inputs(B3, F, K, NB, N, seed=3003)
+  harm = ddsp_b200.Harmonic(n_samples=N)
+  noise = ddsp_b200.FilteredNoise(n_samples=N, window_size=0)
+  group = ddsp_b200.ProcessorGroup(dag=[
+      (harm, ['amps', 'harmonic_distribution', 'f0_hz']),
+      (noise, ['noise_magnitudes']),
+      (ddsp_b200.Add(), ['filtered_noise/signal', 'harmonic/signal'])])
+  noise.injected_noise = torch.from_numpy(inp['noise']).cuda()
+  feats = {k: torch.from_numpy(inp[k]).cuda() for k in
+           ('amps', 'harmonic_distribution', 'f0_hz', 'noise_magnitudes')}
+  audio = _np(group(feats))
+  assert audio.shape == (B3, N)
+  for b in (0, 101, 255):
+    sl = slice(b, b + 1)
+    want = oracle.decoder(inp['amps'][sl], inp['harmonic_distribution'][sl],
+                          inp['f0_hz'][sl], inp['noise_magnitudes'][sl],
+                          inp['noise'][sl], n_samples=N, window_size=0,
+                          dtype=np.float64)['add']['signal']
+    emax, el2 = rel_err(audio[sl], want)
+    assert emax < TOL and el2 < TOL, (b, emax, el2)
+
+
+def _ref_spectral_loss_f64(target, audio):
+  """losses.SpectralLoss (ae.gin weights) per batch item, float64 torch ops:
+  tf.signal.stft(pad_end=True) framing, periodic Hann, |rfft|, L1 on magnitudes and
+  on safe_log magnitudes (losses.py:194-243, spectral_ops.py:34-47)."""
+  total = 0.0
+  for size in (2048, 1024, 512, 256, 128, 64):
+    step = size // 4
+    n = audio.shape[-1]
+    n_frames = -(-n // step)
+    pad = (n_frames - 1) * step + size - n
+    win = torch.hann_window(size, periodic=True, dtype=torch.float64, device=audio.device)
+
+    def mag(x):
+      fr = torch.nn.functional.pad(x, (0, pad)).unfold(-1, size, step)
+      return torch.fft.rfft(fr * win, dim=-1).abs()
+
+    t, v = mag(target), mag(audio)
+    slog = lambda m: torch.log(torch.where(m <= 0, torch.full_like(m, 1e-5), m))
+    total = total + (t - v).abs().mean(dim=(-2, -1)) + (slog(t) - slog(v)).abs().mean(dim=(-2, -1))
+  return total            # [items]
+
+
+def test_c4_batch128_loss_and_gradients():
+  """BASELINE.json configs[3]: decoder forward + backward through the multi-scale
+  SpectralLoss at B=128.  Loss value of a 2-item sub-batch and the B=128 gradients
+  of those two items against float64 autograd of an op-by-op restatement."""
+  from ddsp_b200 import autograd as ag
+  from ddsp_b200 import losses
+  from tests.test_gpu_backward import ref_harmonic, ref_noise
+  B4, items = 128, (5, 77)
+  inp = synth_inputs(B4, F, K, NB, N, seed=4004)
+  dev = torch.device('cuda')
+  raw = {k: torch.from_numpy(inp[k]).to(dev).requires_grad_(True) for k in
+         ('amps', 'harmonic_distribution', 'noise_magnitudes')}
+  f0 = torch.from_numpy(inp['f0_hz']).to(dev)
+  target = 0.1 * torch.randn(B4, N, device=dev, generator=torch.Generator(dev).manual_seed(1))
+  nz = core.uniform_noise(B4, N, seed=9, offset=4)       # the in-kernel Philox stream
+  loss_obj = losses.SpectralLoss(mag_weight=1.0, logmag_weight=1.0)
+  audio = ag.decoder_train(raw['amps'], raw['harmonic_distribution'], f0,
+                           raw['noise_magnitudes'], n_samples=N, window_size=0,
+                           seed=9, offset=4)
+  loss = loss_obj(target, audio)
+  loss.backward()
+
+  idx = torch.tensor(items, device=dev)
+  r64 = {k: v.detach()[idx].double().requires_grad_(True) for k, v in raw.items()}
+  a, h = ag.harmonic_controls(r64['amps'], r64['harmonic_distribution'], f0[idx].double())
+  ref_audio = (ref_harmonic(f0[idx].double(), a, h, N) +
+               ref_noise(ag.exp_sigmoid(r64['noise_magnitudes'] - 5.0), nz[idx].double(), N))
+  emax, el2 = rel_err(_np(audio.detach()[idx]), _np(ref_audio.detach()))
+  assert emax < TOL and el2 < TOL, (emax, el2)
+  per_item = _ref_spectral_loss_f64(target[idx].double(), ref_audio)
+  # value: the same two items as their own batch
+  with torch.no_grad():
+    sub = loss_obj(target[idx], audio.detach()[idx])
+  assert abs(float(sub) - float(per_item.mean())) < 1e-4 * float(per_item.mean())
+  # gradients: loss = mean over items of per-item losses
+  (per_item.sum() / B4).backward()
+  for k in raw:
+    got = raw[k].grad[idx].double()
+    want = r64[k].grad
+    err = float((got - want).abs().max() / want.abs().max())
+    l2 = float(((got - want)**2).sum().sqrt() / (want**2).sum().sqrt())
+    assert err < 5e-3 and l2 < 2e-3, (k, err, l2)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert hasattr(lib, name), name
     assert name in _lib.SIGNATURES, f'{name} is not bound in _lib.SIGNATURES'
   assert set(_lib.SIGNATURES) == set(names)
-  assert _lib.load().ddsp_b200_version() == 100
+  assert _lib.load().ddsp_b200_version() == 200
 
 
 def test_abi_validates_before_launching():
@@ -99,10 +99,9 @@ def test_harmonic_synthesis_value_errors():
     core.harmonic_synthesis(f0, amp, n_samples=5)
   with pytest.raises(ValueError, match='divisible'):         # core.py:687-693
     core.harmonic_synthesis(f0, amp, n_samples=645)
-  with pytest.raises(NotImplementedError):
-    core.harmonic_synthesis(f0, amp, n_samples=640, amp_resample_method='cubic')
-  with pytest.raises(NotImplementedError):
-    core.harmonic_synthesis(f0, amp, harmonic_shifts=f0, n_samples=640)
+  with pytest.raises(ValueError, match='harmonic_shifts'):
+    core.harmonic_synthesis(f0, amp, harmonic_shifts=np.zeros((1, 9, 4), np.float32),
+                            n_samples=640)
 
 
 def test_fft_convolve_value_errors():
