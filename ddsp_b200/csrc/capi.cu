@@ -11,6 +11,7 @@
 #include "harmonic.cuh"
 #include "harmonic_fast.cuh"
 #include "harmonic_v2.cuh"
+#include "harmonic_v3.cuh"
 #include "noise.cuh"
 #include "noise_fused.cuh"
 #include "noise_pipe.cuh"
@@ -61,14 +62,18 @@ static int set_smem(K kernel, size_t bytes, const char* name) {
 using namespace ddsp;
 
 namespace ddsp {
-// v2 is the product kernel; DDSP_B200_HARM_IMPL=fast selects the first-generation
-// kernel for A/B measurements (tools/harm_sweep.py).
+// v3 is the product kernel; DDSP_B200_HARM_IMPL=v2 / fast select the earlier
+// generations for A/B measurements (tools/harm_sweep.py).
 static inline int launch_harmonic_best(const HarmonicParams& p, cudaStream_t st) {
-  static const bool use_fast = [] {
+  static const int impl = [] {
     const char* e = getenv("DDSP_B200_HARM_IMPL");
-    return e != nullptr && strcmp(e, "fast") == 0;
+    if (e != nullptr && strcmp(e, "fast") == 0) return 1;
+    if (e != nullptr && strcmp(e, "v2") == 0) return 2;
+    return 3;
   }();
-  return use_fast ? launch_harmonic_fast(p, st) : launch_harmonic_v2(p, st);
+  if (impl == 1) return launch_harmonic_fast(p, st);
+  if (impl == 2) return launch_harmonic_v2(p, st);
+  return launch_harmonic_v3(p, st);
 }
 }  // namespace ddsp
 
