@@ -162,7 +162,8 @@ def resize_nearest_v1(x, n_out, align_corners=False):
   n_in = x.shape[1]
   if align_corners and n_out > 1:
     scale = np.float32(n_in - 1) / np.float32(n_out - 1)
-    src = np.round(np.arange(n_out, dtype=np.float32) * scale)
+    # C roundf: halves round away from zero (resize_nearest_neighbor_op.cc)
+    src = np.floor(np.arange(n_out, dtype=np.float32) * scale + np.float32(0.5))
   else:
     scale = np.float32(n_in) / np.float32(n_out)
     src = np.floor(np.arange(n_out, dtype=np.float32) * scale)

@@ -992,8 +992,9 @@ def _resize_axis(a, out_size, method, align_corners, axis):
   scale = _resize_scale(in_size, out_size, align_corners)
   src = (np.arange(out_size, dtype=_F32().type) * scale).astype(_F32().type)
   if method == _ResizeMethod.NEAREST_NEIGHBOR:
-    idx = np.minimum((np.rint(src) if align_corners else np.floor(src)).astype(np.int64),
-                     in_size - 1)
+    # roundf (half away from zero), not rint: resize_nearest_neighbor_op.cc
+    idx = np.minimum((np.floor(src + _F32().type(0.5)) if align_corners
+                      else np.floor(src)).astype(np.int64), in_size - 1)
     out = a[idx]
   elif method == _ResizeMethod.BILINEAR:
     lo_f = np.floor(src)
