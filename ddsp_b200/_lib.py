@@ -66,6 +66,11 @@ SIGNATURES = {
               _f, _vp]),
     'ddsp_b200_harmonic_backward':
         (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'ddsp_b200_harmonic_backward_f0':
+        (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
+    'ddsp_b200_harmonic_controls_backward':
+        (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
+    'ddsp_b200_noise_controls_backward': (_i, [_vp, _vp, _vp, _i64, _f, _vp]),
     'ddsp_b200_filtered_noise_backward':
         (_i, [_vp, _vp, _u64, _u64, _vp, _i, _i, _i, _i, _i, _vp]),
     'ddsp_b200_oscillator_bank_workspace': (_sz, [_i, _i, _i]),

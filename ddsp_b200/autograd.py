@@ -5,13 +5,17 @@ The reference differentiates through every TF op of `core.harmonic_synthesis` /
 `core.frequency_filter`; here forward and backward are the hand-written CUDA
 kernels, exposed as `torch.autograd.Function`s:
 
-  * `HarmonicSynthesisFn`  - d amplitudes, d harmonic_distribution (d f0 is not
-    built: in `ae.gin` f0 is data, `training/preprocessing.py:74-91`);
-  * `FilteredNoiseFn`      - d magnitudes (the filter is linear in them).
+  * `HarmonicSynthesisFn`  - d amplitudes, d harmonic_distribution, d f0 (the
+    phase path, `models/inverse_synthesis.py:84-117`; computed only when f0
+    requires grad);
+  * `FilteredNoiseFn`      - d magnitudes (the filter is linear in them);
+  * `DecoderFn` / `decoder_train` - the whole `ae.gin` decoder from RAW network
+    outputs: forward is the fused two-kernel pipeline (`get_controls` in shared
+    memory), backward is the two synthesizer backward kernels plus the
+    `get_controls` backward kernels - no frame-rate torch op on either pass.
 
-`Harmonic.get_controls` / `FilteredNoise.get_controls` (exp_sigmoid, Nyquist
-normalisation) are frame-rate and run as ordinary torch ops on this path, so
-autograd carries the gradient on to the raw network outputs.
+`harmonic_controls` / `exp_sigmoid` below are the same `get_controls` arithmetic as
+differentiable torch ops, kept for callers that compose their own graphs.
 """
 import math
 
@@ -46,12 +50,6 @@ class HarmonicSynthesisFn(torch.autograd.Function):
   def backward(ctx, grad_audio):
     f0_hz, amplitudes, hd = ctx.saved_tensors
     n_samples, sample_rate, method = ctx.cfg
-    if ctx.needs_input_grad[0]:
-      raise NotImplementedError(
-          'HarmonicSynthesisFn: f0_hz requires grad, but the gradient with respect '
-          'to the fundamental frequency is not built (the reference gets it from '
-          'TF autodiff through the phase cumsum).  Detach f0_hz, or differentiate '
-          'core.oscillator_bank-style torch ops for that path.')
     b, f, k = hd.shape
     grad_audio = grad_audio.contiguous().to(torch.float32)
     g0 = torch.empty_like(hd)
@@ -65,7 +63,88 @@ class HarmonicSynthesisFn(torch.autograd.Function):
     dha[:, -1] += g1[:, -1]
     d_hd = dha * amplitudes
     d_amp = (dha * hd).sum(-1, keepdim=True)
-    return None, d_amp, d_hd, None, None, None
+    d_f0 = None
+    if ctx.needs_input_grad[0]:
+      d_f0 = _harmonic_d_f0(f0_hz, amplitudes, hd, grad_audio, n_samples, sample_rate,
+                            method)
+    return d_f0, d_amp, d_hd, None, None, None
+
+
+def _harmonic_d_f0(f0_hz, amplitudes, hd, grad_audio, n_samples, sample_rate, method):
+  """dL/d f0_hz [B, F, 1] through the phase (`ddsp_b200_harmonic_backward_f0`)."""
+  b, f, k = hd.shape
+  d_f0 = torch.empty((b, f, 1), dtype=torch.float32, device=hd.device)
+  nbytes = 12 * b * f
+  ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=hd.device)
+  _lib.check(_lib.load().ddsp_b200_harmonic_backward_f0(
+      f0_hz.data_ptr(), amplitudes.data_ptr(), hd.data_ptr(), grad_audio.data_ptr(),
+      d_f0.data_ptr(), b, f, k, n_samples, sample_rate, core.AMP_METHODS[method],
+      ws.data_ptr(), nbytes, _stream()))
+  return d_f0
+
+
+class DecoderFn(torch.autograd.Function):
+  """The `ae.gin` decoder (ae.gin:47-72) from raw network outputs, forward and
+  backward entirely in the CUDA library.  Gradients: amps, harmonic_distribution,
+  noise_magnitudes always; f0_hz when it requires grad."""
+
+  @staticmethod
+  def forward(ctx, amps, harmonic_distribution, f0_hz, noise_magnitudes, n_samples,
+              sample_rate, amp_resample_method, normalize_below_nyquist, window_size,
+              initial_bias, noise, seed, offset):
+    amps = core.torch_float32(amps)
+    hd = core.torch_float32(harmonic_distribution)
+    f0_hz = core.torch_float32(f0_hz)
+    mags = core.torch_float32(noise_magnitudes)
+    noise = None if noise is None else core.torch_float32(noise)
+    ctx.save_for_backward(amps, hd, f0_hz, mags)
+    ctx.noise = noise
+    ctx.cfg = (int(n_samples), float(sample_rate), amp_resample_method,
+               bool(normalize_below_nyquist), int(window_size), float(initial_bias),
+               int(seed), int(offset))
+    return core.decoder_forward(
+        amps, hd, f0_hz, mags, n_samples, sample_rate=sample_rate,
+        amp_resample_method=amp_resample_method,
+        normalize_below_nyquist=normalize_below_nyquist, window_size=window_size,
+        initial_bias=initial_bias, noise=noise, seed=seed, offset=offset)
+
+  @staticmethod
+  def backward(ctx, grad_audio):
+    amps, hd, f0_hz, mags = ctx.saved_tensors
+    n_samples, sample_rate, method, nyq, window_size, bias, seed, offset = ctx.cfg
+    b, f, k = hd.shape
+    nb = mags.shape[-1]
+    lib = _lib.load()
+    st = _stream()
+    g = grad_audio.contiguous().to(torch.float32)
+    flags = _lib.CTL_SCALE | (_lib.CTL_NYQUIST if nyq else 0)
+    # harmonic: sample-rate reductions, then get_controls transposed at frame rate
+    g0 = torch.empty_like(hd)
+    g1 = torch.empty_like(hd)
+    _lib.check(lib.ddsp_b200_harmonic_backward(
+        f0_hz.data_ptr(), g.data_ptr(), g0.data_ptr(), g1.data_ptr(), b, f, k,
+        n_samples, sample_rate, core.AMP_METHODS[method], st))
+    d_amps = torch.empty_like(amps)
+    d_hd = torch.empty_like(hd)
+    _lib.check(lib.ddsp_b200_harmonic_controls_backward(
+        amps.data_ptr(), hd.data_ptr(), f0_hz.data_ptr(), g0.data_ptr(), g1.data_ptr(),
+        d_amps.data_ptr(), d_hd.data_ptr(), b, f, k, sample_rate, flags, st))
+    # noise: the filter is linear in the magnitudes
+    dmags = torch.empty_like(mags)
+    _lib.check(lib.ddsp_b200_filtered_noise_backward(
+        g.data_ptr(), 0 if ctx.noise is None else ctx.noise.data_ptr(),
+        seed & (2**64 - 1), offset & (2**64 - 1), dmags.data_ptr(), b, f, nb,
+        n_samples, window_size, st))
+    d_mags = torch.empty_like(mags)
+    _lib.check(lib.ddsp_b200_noise_controls_backward(
+        mags.data_ptr(), dmags.data_ptr(), d_mags.data_ptr(), mags.numel(), bias, st))
+    d_f0 = None
+    if ctx.needs_input_grad[2]:
+      # the phase path needs the synthesizer controls: one controls launch
+      a_ctl, h_ctl = core.harmonic_controls(amps, hd, f0_hz, sample_rate, scale=True,
+                                            normalize_below_nyquist=nyq)
+      d_f0 = _harmonic_d_f0(f0_hz, a_ctl, h_ctl, g, n_samples, sample_rate, method)
+    return (d_amps, d_hd, d_f0, d_mags) + (None,) * 9
 
 
 class FilteredNoiseFn(torch.autograd.Function):
@@ -113,10 +192,23 @@ def harmonic_controls(amps, harmonic_distribution, f0_hz, sample_rate=16000,
 
 def decoder_train(amps, harmonic_distribution, f0_hz, noise_magnitudes,
                   n_samples=64000, sample_rate=16000, window_size=0,
-                  initial_bias=-5.0, noise=None, seed=0, offset=0):
+                  initial_bias=-5.0, noise=None, seed=0, offset=0,
+                  amp_resample_method='window', normalize_below_nyquist=True):
   """The `ae.gin` decoder (ae.gin:47-72) with gradients to amps,
-  harmonic_distribution and noise_magnitudes: get_controls in torch, the two
-  synthesizers as CUDA forward / backward kernels, Add in torch."""
+  harmonic_distribution, noise_magnitudes (and f0_hz if it requires grad) - one
+  autograd node: fused forward pipeline, CUDA backward kernels for the two
+  synthesizers and both `get_controls`."""
+  return DecoderFn.apply(amps, harmonic_distribution, f0_hz, noise_magnitudes,
+                         n_samples, sample_rate, amp_resample_method,
+                         normalize_below_nyquist, window_size, initial_bias, noise,
+                         seed, offset)
+
+
+def decoder_train_unfused(amps, harmonic_distribution, f0_hz, noise_magnitudes,
+                          n_samples=64000, sample_rate=16000, window_size=0,
+                          initial_bias=-5.0, noise=None, seed=0, offset=0):
+  """The same decoder with `get_controls` as differentiable torch ops around the two
+  synthesizer Functions (the round-1 route; kept as a cross-check of DecoderFn)."""
   dev = core._device()
   amps = core.torch_float32(amps, dev) if not isinstance(amps, torch.Tensor) else amps
   a, h = harmonic_controls(amps, harmonic_distribution, f0_hz, sample_rate)

@@ -17,6 +17,7 @@
 #include "noise_pipe.cuh"
 #include "host_pipeline.cuh"
 #include "backward.cuh"
+#include "controls_bwd.cuh"
 #include "oscbank.cuh"
 #include "sinusoidal.cuh"
 #include "spectral.cuh"
@@ -652,6 +653,97 @@ int ddsp_b200_harmonic_backward(const float* f0_hz, const float* grad_audio,
     harmonic_backward_kernel<false><<<grid, kHbThreads, smem, st>>>(p, grad_audio, g0, g1);
   }
   DDSP_CHECK_LAUNCH("harmonic_backward");
+  return 0;
+}
+
+int ddsp_b200_harmonic_backward_f0(const float* f0_hz, const float* amps,
+                                   const float* hd, const float* grad_audio,
+                                   float* d_f0, int B, int F, int K, int N,
+                                   float sample_rate, int amp_method,
+                                   void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  DDSP_REQUIRE(f0_hz && amps && grad_audio && d_f0, DDSP_B200_E_INVALID,
+               "harmonic_backward_f0: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && K >= 1 && N >= 1 && N % F == 0, DDSP_B200_E_INVALID,
+               "harmonic_backward_f0: bad shape B=%d F=%d K=%d N=%d", B, F, K, N);
+  DDSP_REQUIRE(hd != nullptr || K == 1, DDSP_B200_E_INVALID,
+               "harmonic_backward_f0: harmonic_distribution is NULL but K=%d", K);
+  DDSP_REQUIRE(amp_method == DDSP_B200_AMP_WINDOW || amp_method == DDSP_B200_AMP_LINEAR,
+               DDSP_B200_E_INVALID, "harmonic_backward_f0: bad amp_method %d", amp_method);
+  DDSP_REQUIRE(sample_rate > 0.f, DDSP_B200_E_INVALID,
+               "harmonic_backward_f0: sample_rate must be positive");
+  if (B == 0) return 0;
+  DDSP_REQUIRE(B <= 65535, DDSP_B200_E_INVALID,
+               "harmonic_backward_f0: B=%d exceeds the 65535 grid limit", B);
+  const size_t need = sizeof(float) * 3 * (size_t)B * F;
+  DDSP_REQUIRE(workspace != nullptr && workspace_bytes >= need, DDSP_B200_E_WORKSPACE,
+               "harmonic_backward_f0: workspace of %zu B needed, %zu given", need,
+               workspace_bytes);
+  HarmonicParams p;
+  p.f0 = f0_hz; p.amps = amps; p.hd = hd; p.audio = nullptr;
+  p.B = B; p.F = F; p.K = K; p.N = N; p.hop = N / F;
+  p.sample_rate = sample_rate; p.nyquist = sample_rate * 0.5f;
+  p.inv_sr = 1.0 / (double)sample_rate;
+  p.amp_method = amp_method; p.accumulate = 0; p.ctl_flags = 0;
+  p.init_phase = nullptr; p.final_phase = nullptr; p.mask_nyquist = 1;
+  p.Kp = (K + 3) & ~3;
+  int FT = std::max(1, std::min(F, 2048 / p.hop));
+  while (FT > 1 && harmonic_df0_smem(FT, p.Kp) > kMaxDynSmem) FT = (FT + 1) / 2;
+  DDSP_REQUIRE(harmonic_df0_smem(FT, p.Kp) <= kMaxDynSmem, DDSP_B200_E_UNSUPPORTED,
+               "harmonic_backward_f0: K=%d needs too much shared memory", K);
+  p.FT = FT;
+  const size_t smem = harmonic_df0_smem(FT, p.Kp);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* sq = reinterpret_cast<float*>(workspace);
+  dim3 grid((F + FT - 1) / FT, B);
+  if (amp_method == DDSP_B200_AMP_WINDOW) {
+    int rc = set_smem(harmonic_df0_kernel<true>, smem, "harmonic_backward_f0");
+    if (rc) return rc;
+    harmonic_df0_kernel<true><<<grid, kDf0Threads, smem, st>>>(p, grad_audio, sq);
+  } else {
+    int rc = set_smem(harmonic_df0_kernel<false>, smem, "harmonic_backward_f0");
+    if (rc) return rc;
+    harmonic_df0_kernel<false><<<grid, kDf0Threads, smem, st>>>(p, grad_audio, sq);
+  }
+  DDSP_CHECK_LAUNCH("harmonic_backward_f0");
+  harmonic_df0_finalize<<<(B + 127) / 128, 128, 0, st>>>(sq, d_f0, B, F, p.hop,
+                                                       (float)p.inv_sr);
+  DDSP_CHECK_LAUNCH("harmonic_backward_f0(finalize)");
+  return 0;
+}
+
+int ddsp_b200_harmonic_controls_backward(const float* amps_raw, const float* hd_raw,
+                                         const float* f0_hz, const float* g0,
+                                         const float* g1, float* d_amps_raw,
+                                         float* d_hd_raw, int B, int F, int K,
+                                         float sample_rate, int flags, void* stream) {
+  DDSP_REQUIRE(amps_raw && hd_raw && f0_hz && g0 && g1 && d_amps_raw && d_hd_raw,
+               DDSP_B200_E_INVALID, "harmonic_controls_backward: null pointer");
+  DDSP_REQUIRE(B >= 0 && F >= 1 && K >= 1, DDSP_B200_E_INVALID,
+               "harmonic_controls_backward: bad shape B=%d F=%d K=%d", B, F, K);
+  const int64_t rows = (int64_t)B * F;
+  if (rows == 0) return 0;
+  DDSP_REQUIRE(rows < (1ll << 31) / 32, DDSP_B200_E_INVALID,
+               "harmonic_controls_backward: B*F too large");
+  const int threads = 256;
+  const int blocks = (int)((rows * 32 + threads - 1) / threads);
+  harmonic_controls_backward_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      amps_raw, hd_raw, f0_hz, g0, g1, d_amps_raw, d_hd_raw, (int)rows, F, K,
+      sample_rate * 0.5f, flags);
+  DDSP_CHECK_LAUNCH("harmonic_controls_backward");
+  return 0;
+}
+
+int ddsp_b200_noise_controls_backward(const float* mags_raw, const float* d_mags,
+                                      float* d_raw, int64_t n, float initial_bias,
+                                      void* stream) {
+  DDSP_REQUIRE(mags_raw && d_mags && d_raw, DDSP_B200_E_INVALID,
+               "noise_controls_backward: null pointer");
+  DDSP_REQUIRE(n >= 0, DDSP_B200_E_INVALID, "noise_controls_backward: n < 0");
+  if (n == 0) return 0;
+  noise_controls_backward_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      mags_raw, d_mags, d_raw, n, initial_bias);
+  DDSP_CHECK_LAUNCH("noise_controls_backward");
   return 0;
 }
 

@@ -205,6 +205,34 @@ int ddsp_b200_harmonic_backward(const float* f0_hz, const float* grad_audio,
                                 float* g0, float* g1, int B, int F, int K, int N,
                                 float sample_rate, int amp_method, void* stream);
 
+/* d f0 of core.harmonic_synthesis (what the reference gets from TF autodiff through
+ * the phase cumsum, core.py:947-958; needed by models/inverse_synthesis.py:84-117).
+ * f0_hz, amps [B,F,1], hd [B,F,K] are synthesizer CONTROLS; grad_audio [B,N] ->
+ * d_f0 [B,F].  workspace: 12 * B * F bytes (per-frame partial sums). */
+int ddsp_b200_harmonic_backward_f0(const float* f0_hz, const float* amps,
+                                   const float* hd, const float* grad_audio,
+                                   float* d_f0, int B, int F, int K, int N,
+                                   float sample_rate, int amp_method,
+                                   void* workspace, size_t workspace_bytes,
+                                   void* stream);
+
+/* Backward of Harmonic.get_controls (synths.py:94-121) fused with the frame-rate
+ * recombination of ddsp_b200_harmonic_backward's g0 / g1: from the RAW network
+ * outputs (amps_raw [B,F,1], hd_raw [B,F,K]) and f0_hz to d amps_raw, d hd_raw -
+ * exp_sigmoid' (core.py:386-404), the Nyquist mask and the row normalisation
+ * (core.py:894-907, 207-210) transposed.  flags as ddsp_b200_harmonic_controls. */
+int ddsp_b200_harmonic_controls_backward(const float* amps_raw, const float* hd_raw,
+                                         const float* f0_hz, const float* g0,
+                                         const float* g1, float* d_amps_raw,
+                                         float* d_hd_raw, int B, int F, int K,
+                                         float sample_rate, int flags, void* stream);
+
+/* Backward of FilteredNoise.get_controls (synths.py:165-179):
+ * d raw = d magnitudes * exp_sigmoid'(raw + initial_bias), n elements. */
+int ddsp_b200_noise_controls_backward(const float* mags_raw, const float* d_mags,
+                                      float* d_raw, int64_t n, float initial_bias,
+                                      void* stream);
+
 /* Backward of FilteredNoise.get_signal w.r.t. magnitudes (controls): the
  * transpose of core.frequency_filter (core.py:1628-1655) for the same noise
  * (caller-supplied, or the Philox stream of (seed, offset)).

@@ -12,7 +12,7 @@ from tests.util import synth_inputs
 pytestmark = pytest.mark.gpu
 
 
-def ref_harmonic(f0, amp, hd, n_samples, sr=16000.0):
+def ref_harmonic(f0, amp, hd, n_samples, sr=16000.0, linear_amp=False):
   """core.harmonic_synthesis (core.py:1048-1111) in float64 torch ops."""
   b, f, k = hd.shape
   hop = n_samples // f
@@ -25,6 +25,8 @@ def ref_harmonic(f0, amp, hd, n_samples, sr=16000.0):
   frac = (r / hop)[None, :, None]
   fe = hf[:, i] + (hf[:, i1] - hf[:, i]) * frac
   w1 = (0.5 - 0.5 * torch.cos(math.pi * r / hop))[None, :, None]
+  if linear_amp:
+    w1 = frac
   ae = ha[:, i] * (1 - w1) + ha[:, i1] * w1
   ae = torch.where(fe >= sr / 2, torch.zeros_like(ae), ae)
   phase = torch.cumsum(fe * (2 * math.pi / sr), dim=1)
@@ -98,6 +100,74 @@ def test_noise_backward_matches_autograd(B, F, nb):
   m4 = mags.clone().requires_grad_(True)
   (ag.FilteredNoiseFn.apply(m4, N, 0, nz, 0, 0) * g).sum().backward()
   assert (m3.grad - m4.grad).abs().max() < 1e-5 * m4.grad.abs().max()
+
+
+@pytest.mark.parametrize('B,F,K', [(2, 20, 12), (1, 33, 100), (2, 9, 7)])
+@pytest.mark.parametrize('method', ['window', 'linear'])
+def test_harmonic_backward_f0_matches_autograd(B, F, K, method):
+  """d f0 through the phase (what TF autodiff gives the reference through
+  resample + cumsum + sin, core.py:947-958) against float64 autograd."""
+  N = F * 64
+  inp = synth_inputs(B, F, K, 65, N, seed=K + 3, f0_hi=700.0)
+  dev = torch.device('cuda')
+  f0 = torch.from_numpy(inp['f0_hz']).to(dev)
+  amp = torch.rand(B, F, 1, device=dev) + 0.2
+  hd = torch.rand(B, F, K, device=dev)
+  hd = hd / hd.sum(-1, keepdim=True)
+  g = torch.randn(B, N, device=dev)
+  f1 = f0.clone().requires_grad_(True)
+  out = ag.HarmonicSynthesisFn.apply(f1, amp, hd, N, 16000, method)
+  (out * g).sum().backward()
+  f2 = f0.double().requires_grad_(True)
+  if method == 'window':
+    ref = ref_harmonic(f2, amp.double(), hd.double(), N)
+  else:
+    ref = ref_harmonic(f2, amp.double(), hd.double(), N, linear_amp=True)
+  (ref * g.double()).sum().backward()
+  err = (f1.grad.double() - f2.grad).abs().max() / f2.grad.abs().max()
+  l2 = ((f1.grad.double() - f2.grad)**2).sum().sqrt() / (f2.grad**2).sum().sqrt()
+  assert err < 5e-4 and l2 < 2e-4, (float(err), float(l2))
+
+
+@pytest.mark.parametrize('B,F,K,nb,nyq', [(2, 30, 100, 65, True), (3, 17, 33, 65, True),
+                                          (2, 12, 20, 65, False)])
+def test_decoder_fn_matches_float64_autograd_from_raw_outputs(B, F, K, nb, nyq):
+  """DecoderFn: fused forward + the get_controls backward kernels, against float64
+  autograd of the op-by-op restatement from the RAW network outputs (f0 included)."""
+  N = F * 64
+  inp = synth_inputs(B, F, K, nb, N, seed=F, f0_hi=1200.0)
+  dev = torch.device('cuda')
+  raw = {k: torch.from_numpy(inp[k]).to(dev) for k in
+         ('amps', 'harmonic_distribution', 'f0_hz', 'noise_magnitudes')}
+  nz = torch.from_numpy(inp['noise']).to(dev)
+  g = torch.randn(B, N, device=dev)
+  r32 = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+  out = ag.decoder_train(r32['amps'], r32['harmonic_distribution'], r32['f0_hz'],
+                         r32['noise_magnitudes'], n_samples=N, window_size=0, noise=nz,
+                         normalize_below_nyquist=nyq)
+  (out * g).sum().backward()
+  r64 = {k: v.double().requires_grad_(True) for k, v in raw.items()}
+  a, h = ag.harmonic_controls(r64['amps'], r64['harmonic_distribution'], r64['f0_hz'],
+                              normalize_below_nyquist=nyq)
+  ref = (ref_harmonic(r64['f0_hz'], a, h, N) +
+         ref_noise(ag.exp_sigmoid(r64['noise_magnitudes'] - 5.0), nz.double(), N))
+  (ref * g.double()).sum().backward()
+  assert (out.double() - ref).abs().max() < 1e-4 * ref.abs().max()
+  for k in raw:
+    got, want = r32[k].grad.double(), r64[k].grad
+    err = float((got - want).abs().max() / want.abs().max())
+    l2 = float(((got - want)**2).sum().sqrt() / (want**2).sum().sqrt())
+    assert err < 1e-3 and l2 < 3e-4, (k, err, l2)
+  # and the round-1 route (torch get_controls around the two Functions) agrees
+  r3 = {k: v.clone().requires_grad_(k != 'f0_hz') for k, v in raw.items()}
+  if nyq:
+    out3 = ag.decoder_train_unfused(r3['amps'], r3['harmonic_distribution'], r3['f0_hz'],
+                                    r3['noise_magnitudes'], n_samples=N, window_size=0,
+                                    noise=nz)
+    (out3 * g).sum().backward()
+    for k in ('amps', 'harmonic_distribution', 'noise_magnitudes'):
+      d = (r3[k].grad - r32[k].grad).abs().max() / r32[k].grad.abs().max()
+      assert float(d) < 5e-4, (k, float(d))
 
 
 def test_decoder_train_step_through_spectral_loss():
