@@ -761,11 +761,11 @@ def _crop_range(total_size, audio_size, ir_size, padding, delay_compensation):
   return start, len(rng), crop_size
 
 
-# Impulse responses longer than this take the FFT formulation (cuFFT through
-# torch.fft) instead of the direct-form FIR kernel: the direct form costs
-# audio_size * ir_size MACs per item, the framed FFT convolution O(N log N) - the
-# cross-over is a few thousand taps.  This is the Reverb case (48000-tap IR,
-# effects.py:28-117).
+# Impulse responses longer than this take a frequency-domain formulation instead of
+# the direct-form FIR kernel: the direct form costs audio_size * ir_size MACs per
+# item - the cross-over is a few thousand taps.  One long IR per item (the Reverb
+# case: 48000 taps, effects.py:28-117) runs the hand-written
+# partitioned overlap-save convolution `ddsp_b200_fft_convolve_lti`.
 FFT_CONVOLVE_MIN_IR = 2048
 
 
@@ -833,7 +833,31 @@ def fft_convolve(audio, impulse_response, padding: Text = 'same',
         f'(start={start}, total={total_size}, crop={crop_size}).')
   audio = torch_float32(audio)
   impulse_response = torch_float32(impulse_response).reshape(si)
+  if ir_size >= FFT_CONVOLVE_MIN_IR and n_ir_frames == 1:
+    # one long impulse response per item (effects.Reverb): hand-written
+    # partitioned overlap-save convolution (csrc/longconv.cuh)
+    ir2 = impulse_response.reshape(ir_batch, ir_size).contiguous()
+    if out is None:
+      out = torch.empty((batch_size, crop_size), dtype=torch.float32,
+                        device=audio.device)
+      accumulate = False
+    else:
+      _check_out(out, (batch_size, crop_size), audio)
+    _no_grad_path('fft_convolve', audio, ir2)
+    lib = _lib.load()
+    with _on_device_of(audio, ir2, out):
+      nbytes = lib.ddsp_b200_fft_convolve_lti_workspace(batch_size, audio_size,
+                                                       ir_size, ir_batch)
+      ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=audio.device)
+      _lib.check(lib.ddsp_b200_fft_convolve_lti(
+          _ptr(audio), _ptr(ir2), _ptr(out), batch_size, audio_size, ir_size,
+          ir_batch, int(start), int(crop_size), int(bool(accumulate)), _ptr(ws),
+          nbytes, _stream()))
+    return out
   if ir_size >= FFT_CONVOLVE_MIN_IR:
+    # time-varying filter with long impulse responses (several IR frames of >= 2048
+    # taps): no reference configuration does this; the reference's own framed
+    # algorithm on cuFFT
     wet = _fft_convolve_cufft(audio, impulse_response, n_ir_frames, frame_size,
                               fft_size, int(start), int(crop_size))
     if out is None:

@@ -20,6 +20,7 @@
 #include "controls_bwd.cuh"
 #include "oscbank.cuh"
 #include "sinusoidal.cuh"
+#include "longconv.cuh"
 #include "spectral.cuh"
 
 namespace ddsp {
@@ -836,6 +837,58 @@ int ddsp_b200_oscillator_bank(const float* frequency_envelopes,
         frequency_envelopes, amplitude_envelopes, sums, out, N, K, n_chunks, inv_sr,
         sample_rate * 0.5f);
   DDSP_CHECK_LAUNCH("oscillator_bank(apply)");
+  return 0;
+}
+
+size_t ddsp_b200_fft_convolve_lti_workspace(int B, int N, int S, int ir_batch) {
+  if (B <= 0 || N <= 0 || S <= 0 || (ir_batch != 1 && ir_batch != B)) return 0;
+  const lc::Geom g = lc::geom(N, S);
+  const size_t z = (size_t)B * g.n_in * lc::M, h = (size_t)ir_batch * g.P * lc::M,
+               w = (size_t)B * g.w_len;
+  return sizeof(float2) * (z + h + w) + 256;
+}
+
+int ddsp_b200_fft_convolve_lti(const float* audio, const float* impulse_response,
+                               float* out, int B, int N, int S, int ir_batch,
+                               int start, int out_len, int accumulate,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  DDSP_REQUIRE(audio && impulse_response && out, DDSP_B200_E_INVALID,
+               "fft_convolve_lti: null pointer");
+  DDSP_REQUIRE(B >= 0 && N >= 1 && S >= 1, DDSP_B200_E_INVALID,
+               "fft_convolve_lti: bad shape B=%d N=%d S=%d", B, N, S);
+  // core.py:1441-1443
+  DDSP_REQUIRE(ir_batch == B || ir_batch == 1, DDSP_B200_E_INVALID,
+               "Batch size of audio (%d) and impulse response (%d) must be the same.",
+               B, ir_batch);
+  DDSP_REQUIRE(start >= 0 && out_len >= 0 &&
+                   (long long)start + out_len <= (long long)N + S - 1,
+               DDSP_B200_E_INVALID,
+               "fft_convolve_lti: crop [%d, %d) leaves the convolution of length %lld",
+               start, start + out_len, (long long)N + S - 1);
+  if (B == 0 || out_len == 0) return 0;
+  DDSP_REQUIRE(B <= 65535, DDSP_B200_E_INVALID,
+               "fft_convolve_lti: B=%d exceeds the 65535 grid limit", B);
+  const size_t need = ddsp_b200_fft_convolve_lti_workspace(B, N, S, ir_batch);
+  DDSP_REQUIRE(workspace != nullptr && workspace_bytes >= need, DDSP_B200_E_WORKSPACE,
+               "fft_convolve_lti: workspace of %zu B needed, %zu given", need,
+               workspace_bytes);
+  const lc::Geom g = lc::geom(N, S);
+  float2* Z = reinterpret_cast<float2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float2* H = Z + (size_t)B * g.n_in * lc::M;
+  float2* W = H + (size_t)ir_batch * g.P * lc::M;
+  cudaStream_t st = (cudaStream_t)stream;
+  lc::lc_fft_blocks<<<dim3(g.P, ir_batch), lc::THREADS, 0, st>>>(impulse_response, H, S,
+                                                                0, g.P, 1);
+  DDSP_CHECK_LAUNCH("fft_convolve_lti(ir spectra)");
+  lc::lc_fft_blocks<<<dim3(g.n_in, B), lc::THREADS, 0, st>>>(audio, Z, N, g.n2, g.n_in, 0);
+  DDSP_CHECK_LAUNCH("fft_convolve_lti(audio spectra)");
+  lc::lc_mac_ifft<<<dim3(g.n_out, B), lc::THREADS, 0, st>>>(
+      Z, H, W, g.n_in, g.P, g.n_out, ir_batch == 1 ? 0 : g.P * lc::M);
+  DDSP_CHECK_LAUNCH("fft_convolve_lti(multiply-accumulate + inverse)");
+  const int cgrid = std::min((out_len + 255) / 256, 8 * kNumSMs);
+  lc::lc_combine<<<dim3(cgrid, B), 256, 0, st>>>(W, out, g.n2, g.w_len, start, out_len,
+                                               N + S - 1, accumulate);
+  DDSP_CHECK_LAUNCH("fft_convolve_lti(combine)");
   return 0;
 }
 

@@ -65,6 +65,66 @@ using hv2::osc_finish;
 using hv2::phase32;
 using hv2::mask4;
 
+// Harmonic.get_controls for up to four rows (r0 .. r0+3 of this warp's block) in
+// shared memory, 8 lanes per row: exp_sigmoid on the live prefix, zeros above it,
+// row normalisation with safe_divide (synths.py:110-117, core.py:894-907).  Same
+// arithmetic as hv2::controls_rows; the values stay in registers between the sum
+// and the normalisation (one store instead of store / load / store), only as many
+// 8-group passes run as the longest of the four rows needs (usually one), and the
+// zero fill of the masked tail is a separate tight loop.  Rows of up to 128
+// harmonics; wider rows take hv2::controls_rows.
+__device__ __forceinline__ void controls_rows4(float* __restrict__ sXw,
+                                               const int* __restrict__ sLive, int r0,
+                                               int nrows, int Kp, bool raw_scale,
+                                               int lane) {
+  const int K4 = Kp >> 2;
+  const int sub = lane >> 3, l8 = lane & 7;
+  const int r = r0 + sub;
+  const bool row_ok = r < nrows;
+  float4* row4 = reinterpret_cast<float4*>(sXw + (row_ok ? r : r0) * Kp);
+  const int live = row_ok ? sLive[r] : 0;
+  const int live4 = (live + 3) >> 2;                 // float4 groups with a live element
+  const int n_it = (__reduce_max_sync(0xffffffffu, live4) + 7) >> 3;   // warp-uniform
+  float4 v[4];
+  float sum = 0.f;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (it < n_it) {
+      const int c4 = l8 + 8 * it;
+      if (c4 < live4) {
+        const float4 x = row4[c4];
+        float e[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float w = e[u];
+          if (raw_scale) w = exp_sigmoid_f(w);
+          if (4 * c4 + u >= live) w = 0.f;
+          e[u] = w;
+          sum += w;
+        }
+        v[it] = make_float4(e[0], e[1], e[2], e[3]);
+      }
+    }
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  const float inv = 1.0f / ((sum == 0.0f) ? 1e-7f : sum);
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (it < n_it) {
+      const int c4 = l8 + 8 * it;
+      if (c4 < live4)
+        row4[c4] = make_float4(v[it].x * inv, v[it].y * inv, v[it].z * inv, v[it].w * inv);
+    }
+  }
+  if (row_ok) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c4 = live4 + l8; c4 < K4; c4 += 8) row4[c4] = z;
+  }
+}
+
 // osc_init without zeroing the accumulators (the first group writes them).
 __device__ __forceinline__ void osc_seed(Osc& st, uint32_t p,
                                          const float2* __restrict__ tab) {
@@ -359,8 +419,13 @@ harmonic_v3_kernel(HarmonicParams p, int use_tma, int FW) {
     int nrows = nfw;
     if (last && rows_in > nfr) nrows = nfw + 1;         // the real row after the tile
     if (have_ctl) {
-      for (int r0 = 0; r0 < nrows; r0 += 4)
-        hv2::controls_rows(sXw, sLive, r0, nrows, Kp, raw_scale, lane);
+      if (Kp <= 128) {
+        for (int r0 = 0; r0 < nrows; r0 += 4)
+          controls_rows4(sXw, sLive, r0, nrows, Kp, raw_scale, lane);
+      } else {
+        for (int r0 = 0; r0 < nrows; r0 += 4)
+          hv2::controls_rows(sXw, sLive, r0, nrows, Kp, raw_scale, lane);
+      }
     }
     if (last && rows_in < nfr + 1) {                    // frame F := frame F-1
       __syncwarp();

@@ -1,0 +1,184 @@
+// core.fft_convolve for ONE long impulse response per item (the LTI case of
+// core.py:1382-1473: effects.Reverb, effects.py:103-117 - 48000 taps on 64000
+// samples).  The direct form costs N * S MACs (3e9 per item), so this one really is
+// a frequency-domain convolution - hand-written: uniformly partitioned
+// overlap-save with L = 1024-sample blocks and 2048-point complex FFTs in shared
+// memory (the reference takes three 131072-point FFTs per item through cuFFT).
+//
+//   * REAL -> COMPLEX PACKING WITHOUT WASTE.  Convolution with a real h is linear
+//     over complex inputs, so the two time-halves of an item ride in one complex
+//     signal: z[n] = x[n] + i x[n + N2], w = z * h, y[n] = Re w[n] + Im w[n - N2].
+//   * NO BIT REVERSAL.  The forward transform is decimation-in-frequency (natural
+//     in, bit-reversed out), the inverse decimation-in-time (bit-reversed in,
+//     natural out); the spectra only ever meet in element-wise products, so both
+//     sides simply live in bit-reversed order.
+//   * Overlap-save: input window j = samples [(j-1) L, (j+1) L) of z; IR partition
+//     p = h[p L, (p+1) L) zero-padded to 2 L; output block j = last L samples of
+//     IFFT(sum_p Z_{j-p} H_p).
+// Kernels: lc_fft_blocks (windows of z, or partitions of h -> spectra),
+// lc_mac_ifft (spectral multiply-accumulate over the partitions + inverse FFT ->
+// w blocks), lc_combine (Re / Im recombination, delay crop, optional accumulate).
+#pragma once
+#include "common.cuh"
+
+namespace ddsp {
+namespace lc {
+
+constexpr int L = 1024;          // block length
+constexpr int M = 2 * L;         // FFT size
+constexpr int LOGM = 11;
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+
+// tw[m] = exp(-2 pi i m / M), m < M / 2
+__device__ __forceinline__ void fill_twiddles(float2* tw, int tid) {
+  for (int m = tid; m < M / 2; m += THREADS) {
+    float s, c;
+    sincospif(-2.0f * (float)m / (float)M, &s, &c);
+    tw[m] = make_float2(c, s);
+  }
+}
+
+// forward, decimation in frequency: natural order in, bit-reversed order out
+__device__ __forceinline__ void fft_dif(float2* s, const float2* tw, int tid) {
+#pragma unroll 1
+  for (int half = M / 2, sh = 0; half >= 1; half >>= 1, ++sh) {
+    __syncthreads();
+    for (int i = tid; i < M / 2; i += THREADS) {
+      const int k = i & (half - 1);
+      const int a = ((i - k) << 1) + k, b = a + half;
+      const float2 u = s[a], v = s[b];
+      s[a] = make_float2(u.x + v.x, u.y + v.y);
+      s[b] = cmul(make_float2(u.x - v.x, u.y - v.y), tw[k << sh]);
+    }
+  }
+  __syncthreads();
+}
+
+// inverse (unscaled), decimation in time: bit-reversed order in, natural order out
+__device__ __forceinline__ void ifft_dit(float2* s, const float2* tw, int tid) {
+#pragma unroll 1
+  for (int half = 1, sh = LOGM - 1; half <= M / 2; half <<= 1, --sh) {
+    __syncthreads();
+    for (int i = tid; i < M / 2; i += THREADS) {
+      const int k = i & (half - 1);
+      const int a = ((i - k) << 1) + k, b = a + half;
+      const float2 u = s[a], v = cmul_conj(s[b], tw[k << sh]);
+      s[a] = make_float2(u.x + v.x, u.y + v.y);
+      s[b] = make_float2(u.x - v.x, u.y - v.y);
+    }
+  }
+  __syncthreads();
+}
+
+// mode 0: window j of z (two time-halves of audio item b packed as re / im);
+// mode 1: partition p of the impulse response of item b (real, zero-padded).
+// grid (n_blocks, items).
+__global__ void __launch_bounds__(THREADS)
+lc_fft_blocks(const float* __restrict__ src, float2* __restrict__ spec, int len,
+              int n2, int n_blocks, int mode) {
+  __shared__ float2 s[M];
+  __shared__ float2 tw[M / 2];
+  const int tid = threadIdx.x, j = blockIdx.x, b = blockIdx.y;
+  const float* x = src + (size_t)b * len;
+  fill_twiddles(tw, tid);
+  for (int i = tid; i < M; i += THREADS) {
+    float re = 0.f, im = 0.f;
+    if (mode == 0) {
+      const long long n = (long long)(j - 1) * L + i;          // index into z
+      if (n >= 0 && n < n2) {
+        re = x[n];
+        if (n + n2 < len) im = x[n + n2];
+      }
+    } else if (i < L) {
+      const long long n = (long long)j * L + i;
+      if (n < len) re = x[n];
+    }
+    s[i] = make_float2(re, im);
+  }
+  fft_dif(s, tw, tid);
+  float2* out = spec + ((size_t)b * n_blocks + j) * M;
+  for (int i = tid; i < M; i += THREADS) out[i] = s[i];
+}
+
+// w block j of item b: IFFT(sum_p Z[b, j - p] H[bi, p]) -> last L samples.
+// grid (n_out_blocks, B).  Z: [B, n_in, M], H: [Bi, P, M], W: [B, n_out * L].
+__global__ void __launch_bounds__(THREADS)
+lc_mac_ifft(const float2* __restrict__ Z, const float2* __restrict__ H,
+            float2* __restrict__ W, int n_in, int P, int n_out, int ir_batch_stride) {
+  __shared__ float2 s[M];
+  __shared__ float2 tw[M / 2];
+  const int tid = threadIdx.x, j = blockIdx.x, b = blockIdx.y;
+  fill_twiddles(tw, tid);
+  float2 acc[M / THREADS];
+#pragma unroll
+  for (int e = 0; e < M / THREADS; ++e) acc[e] = make_float2(0.f, 0.f);
+  const float2* Zb = Z + (size_t)b * n_in * M;
+  const float2* Hb = H + (size_t)b * ir_batch_stride;
+  const int p_lo = max(0, j - (n_in - 1)), p_hi = min(P - 1, j);
+  for (int p = p_lo; p <= p_hi; ++p) {
+    const float2* zp = Zb + (size_t)(j - p) * M;
+    const float2* hp = Hb + (size_t)p * M;
+#pragma unroll
+    for (int e = 0; e < M / THREADS; ++e) {
+      const int f = tid + e * THREADS;
+      const float2 z = zp[f], h = hp[f];
+      acc[e].x = fmaf(z.x, h.x, fmaf(-z.y, h.y, acc[e].x));
+      acc[e].y = fmaf(z.x, h.y, fmaf(z.y, h.x, acc[e].y));
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < M / THREADS; ++e) s[tid + e * THREADS] = acc[e];
+  ifft_dit(s, tw, tid);
+  const float scale = 1.0f / (float)M;
+  float2* out = W + ((size_t)b * n_out + j) * L;
+  for (int i = tid; i < L; i += THREADS) {
+    const float2 v = s[L + i];
+    out[i] = make_float2(v.x * scale, v.y * scale);
+  }
+}
+
+// y[b, n] = Re w[n + start] + Im w[n + start - N2], n < out_len (crop of
+// crop_and_compensate_delay, core.py:1338-1379).  w is valid on [0, n_out * L).
+__global__ void __launch_bounds__(256)
+lc_combine(const float2* __restrict__ W, float* __restrict__ out, int n2, int w_len,
+           int start, int out_len, int total_len, int accumulate) {
+  const int b = blockIdx.y;
+  const float2* w = W + (size_t)b * w_len;
+  float* o = out + (size_t)b * out_len;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < out_len;
+       n += gridDim.x * blockDim.x) {
+    const int t = n + start;                   // position in the full convolution
+    float v = 0.f;
+    if (t < total_len) {
+      if (t < w_len) v = w[t].x;
+      const int u = t - n2;
+      if (u >= 0 && u < w_len) v += w[u].y;
+    }
+    if (accumulate) v += o[n];
+    o[n] = v;
+  }
+}
+
+struct Geom {
+  int n2, n_in, P, n_out, w_len;
+};
+__host__ inline Geom geom(int N, int S) {
+  Geom g;
+  g.n2 = (N + 1) / 2;
+  g.n_in = (g.n2 + L - 1) / L + 1;             // windows with any non-zero sample
+  g.P = (S + L - 1) / L;
+  // w = z * h has n2 + S - 1 samples
+  g.n_out = (g.n2 + S - 1 + L - 1) / L;
+  g.w_len = g.n_out * L;
+  return g;
+}
+
+}  // namespace lc
+}  // namespace ddsp

@@ -253,6 +253,19 @@ int ddsp_b200_oscillator_bank(const float* frequency_envelopes,
                               void* workspace, size_t workspace_bytes,
                               void* stream);
 
+/* core.fft_convolve (core.py:1382-1473) with ONE impulse response per item of any
+ * length (the LTI case: effects.Reverb, effects.py:103-117, 48000 taps): uniformly
+ * partitioned overlap-save convolution, 1024-sample blocks, hand-written 2048-point
+ * FFTs.  audio [B,N], impulse_response [ir_batch (1 or B), S] -> out [B,out_len] =
+ * full convolution [start, start + out_len) (crop_and_compensate_delay,
+ * core.py:1338-1379; start + out_len <= N + S - 1).  workspace:
+ * ddsp_b200_fft_convolve_lti_workspace(B, N, S, ir_batch) bytes. */
+size_t ddsp_b200_fft_convolve_lti_workspace(int B, int N, int S, int ir_batch);
+int ddsp_b200_fft_convolve_lti(const float* audio, const float* impulse_response,
+                               float* out, int B, int N, int S, int ir_batch,
+                               int start, int out_len, int accumulate,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* core.angular_cumsum (core.py:799-866) and tf.cumsum (core.py:955) on
  * [B,N,C] float32 (C = product of the trailing axes).  mode:
  *   0  exact: the wrapped running sum in 64-bit fixed point (what angular_cumsum

@@ -92,3 +92,33 @@ def test_trainable_reverb_and_fir_filter():
   want = o.frequency_filter(audio, scaled, window_size=257)
   emax, el2 = rel_err(got, want)
   assert emax < 1e-4 and el2 < 1e-4, (emax, el2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,n,taps,ir_batch,padding,delay', [
+    (2, 64000, 48000, 2, 'same', 0),        # effects.Reverb at the ae.gin length
+    (3, 64000, 48000, 1, 'same', 0),        # one trainable IR shared by the batch
+    (2, 16000, 2048, 2, 'same', -1),        # smallest IR on this route, auto delay
+    (2, 5000, 9000, 2, 'valid', -1),        # IR longer than the audio, full tail
+    (1, 1023, 2049, 1, 'same', 0),          # ragged against the 1024-sample blocks
+    (2, 4097, 4096, 2, 'valid', 5)])
+def test_long_impulse_response_convolution_kernel(B, n, taps, ir_batch, padding, delay):
+  """`ddsp_b200_fft_convolve_lti` (partitioned overlap-save, hand-written FFTs)
+  behind core.fft_convolve for 2-D / single-frame impulse responses >= 2048 taps,
+  against the oracle's restatement of core.py:1382-1473."""
+  from tests.util import rel_err
+  rng = np.random.default_rng(n + taps)
+  audio = rng.standard_normal((B, n)).astype(np.float32)
+  ir = (rng.standard_normal((ir_batch, taps)) * np.exp(-np.arange(taps) / (taps / 5.0))
+        ).astype(np.float32)
+  want = o.fft_convolve(audio, np.broadcast_to(ir, (B, taps)) if ir_batch == 1 else ir,
+                        padding=padding, delay_compensation=delay)
+  got = core.fft_convolve(audio, ir, padding=padding, delay_compensation=delay)
+  assert tuple(got.shape) == want.shape
+  emax, el2 = rel_err(got.cpu().numpy(), want)
+  assert emax < 1e-4 and el2 < 1e-4, (emax, el2)
+  # accumulate into an existing buffer (the wet + dry sum of Reverb)
+  base = torch.full(tuple(got.shape), 0.25, device='cuda')
+  acc = core.fft_convolve(audio, ir, padding=padding, delay_compensation=delay,
+                          out=base.clone(), accumulate=True)
+  assert float((acc - (got + 0.25)).abs().max()) < 1e-5
