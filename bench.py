@@ -662,6 +662,233 @@ def run_ours(args):
   return line
 
 
+# ----------------------------------------------------------------------------
+# configs[3]: decoder forward + backward through the multi-scale SpectralLoss
+# ----------------------------------------------------------------------------
+C4_BATCH = 128
+
+
+def c4_cpu_throughput(items, repeats=1):
+  """samples/s of oracle/ref_port_torch.train_step on `items` batch items."""
+  import torch
+  from oracle import ref_port_torch as rp
+  torch.set_num_threads(_pick_cpu_threads(min(items, 8)))
+  inp = make_host_inputs(items, seed=97)
+  t = {k: torch.from_numpy(v) for k, v in inp.items()}
+  target = 0.1 * torch.randn(items, N_SAMPLES)
+  best = None
+  for _ in range(repeats):
+    t0 = time.perf_counter()
+    rp.train_step(t['amps'], t['harmonic_distribution'], t['f0_hz'],
+                  t['noise_magnitudes'], target, n_samples=N_SAMPLES)
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+  return items * N_SAMPLES / best, best, torch.get_num_threads()
+
+
+def run_c4_reference(args):
+  if int(os.environ.get('RANK', '0')) != 0:
+    return None
+  n_calls = args.warmup + args.steps
+  items = max(1, min(4, int(150.0 / (2.5 * n_calls))))
+  times = []
+  cores = 0
+  for i in range(n_calls):
+    _, dt, cores = c4_cpu_throughput(items)
+    if i >= args.warmup:
+      times.append(dt)
+  value = items * N_SAMPLES * len(times) / sum(times)
+  return {
+      'impl': 'reference', 'metric': 'audio samples/sec (decoder forward+backward '
+      'through multi-scale SpectralLoss)', 'value': value, 'unit': 'samples/s',
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': 1e3 * sum(times) / len(times), 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': 'configs[3]: decoder fwd+bwd through SpectralLoss (FFT '
+                             '64-2048), N=64000; each step is a bounded sample of %d of '
+                             'the 128 batch items' % items, 'batch_per_step': items},
+      'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                       'sample': '%d of the 128 batch items per step (torch-CPU port, '
+                                 'torch autograd for the backward)' % items},
+      'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0}
+
+
+def run_c4(args):
+  """BASELINE.json configs[3] as its own bench line: `--config c4`."""
+  import torch
+  import torch.distributed as dist
+  from ddsp_b200 import _lib, autograd as ag, host as host_mod, losses, spectral_ops
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py (ours) needs a CUDA device; there is no CPU path.')
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  host_mod.bind_to_device_numa_node(dev)
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    import datetime
+    dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=300))
+  lib = _lib.load()
+  B = C4_BATCH
+  keys = ('amps', 'harmonic_distribution', 'f0_hz', 'noise_magnitudes')
+  grad_keys = ('amps', 'harmonic_distribution', 'noise_magnitudes')
+  host = make_host_inputs(B, seed=55 + rank)
+  sets = []
+  for s in range(3):                      # 3 x 151 MB of inputs + targets > 2x L2
+    d = {k: torch.from_numpy(host[k]).to(dev) for k in keys}
+    if s:
+      d['amps'] = d['amps'] + 0.01 * s
+    for k in grad_keys:
+      d[k].requires_grad_(True)
+    d['target'] = 0.1 * torch.randn(B, N_SAMPLES, device=dev)
+    sets.append(d)
+  pinned = {k: torch.from_numpy(host[k]).pin_memory() for k in keys}
+  pinned['target'] = (0.1 * torch.randn(B, N_SAMPLES)).pin_memory()
+  h2d_bytes = sum(v.numel() * 4 for v in pinned.values())
+  loss_obj = losses.SpectralLoss(mag_weight=1.0, logmag_weight=1.0)
+  last = {}
+
+  def step(i, d=None):
+    d = sets[i % len(sets)] if d is None else d
+    for k in grad_keys:
+      d[k].grad = None
+    audio = ag.decoder_train(d['amps'], d['harmonic_distribution'], d['f0_hz'],
+                             d['noise_magnitudes'], n_samples=N_SAMPLES, window_size=0,
+                             seed=1 + rank, offset=i)
+    loss = loss_obj(d['target'], audio)
+    loss.backward()
+    last['loss'] = loss
+    return loss
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  def timed(fn, steps, warmup):
+    for i in range(warmup):
+      fn(i)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+      fn(warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      t = torch.tensor([ms], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms
+
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  c0 = lib.ddsp_b200_launch_count()
+  sampler.mark_timed(0)
+  ms_step = timed(step, args.steps, args.warmup) / args.steps
+  sampler.mark_timed(1)
+  launches = (lib.ddsp_b200_launch_count() - c0) * args.steps // (args.steps + args.warmup)
+  value = world * B * N_SAMPLES / (ms_step * 1e-3)
+
+  # e2e: host network outputs + target in, loss value out (gradients stay on the GPU)
+  loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+  def step_e2e(i):
+    d = {k: pinned[k].to(dev, non_blocking=True) for k in pinned}
+    for k in grad_keys:
+      d[k].requires_grad_(True)
+    loss = step(i, d)
+    loss_host.copy_(loss.detach(), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+  e2e_steps = max(5, min(args.steps, 20))
+  ms_e2e = timed(step_e2e, e2e_steps, 3) / e2e_steps
+
+  # dominant kernel of the step: the one-pass L1 magnitude / log-magnitude kernel
+  # (18 launches per step, the largest share of the GPU time); timed alone on the
+  # 2048-point STFTs, algorithmic bytes = two complex spectra in, one out
+  size = 2048
+  xt = spectral_ops.stft_cuda(sets[0]['target'], size).contiguous()
+  xvs = [spectral_ops.stft_cuda(sets[i]['target'] * (1.0 + i), size).contiguous()
+         for i in range(3)]
+  sums = torch.zeros(2, dtype=torch.float64, device=dev)
+  m = xt.numel()
+  st_ptr = torch.cuda.current_stream().cuda_stream
+
+  def l1_only(i):
+    x = xvs[i % 3]
+    _lib.check(lib.ddsp_b200_spectral_l1(xt.data_ptr(), x.data_ptr(), x.data_ptr(),
+                                         sums.data_ptr(), m, 1.0, 1.0, xt.shape[-1],
+                                         size, st_ptr))
+  for i in range(5):
+    l1_only(i)
+  torch.cuda.synchronize()
+  e0 = torch.cuda.Event(enable_timing=True)
+  e1 = torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(24):
+    l1_only(i)
+  e1.record()
+  torch.cuda.synchronize()
+  ms_l1 = e0.elapsed_time(e1) / 24
+  clocks = sampler.stop() if rank == 0 else None
+  if rank != 0:
+    if world > 1:
+      dist.barrier()
+      dist.destroy_process_group()
+    return None
+  peak, peak_src = _measured_peaks()
+  l1_bytes = 3 * 8 * m
+  cpu = None
+  if not args.no_cpu_baseline and world == 1:
+    rate, dt, cores = c4_cpu_throughput(2)
+    cpu = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+           'sample': '2 of the %d batch items, forward + backward (torch-CPU port of '
+                     'ddsp core/synths/losses, torch autograd; %.2f s)' % (B, dt)}
+  line = {
+      'metric': 'audio samples/sec (decoder forward+backward through multi-scale '
+                'SpectralLoss)',
+      'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': 'configs[3]: ae.gin decoder forward + backward through '
+                             'SpectralLoss (L1 mag + log-mag, FFT 2048..64), batch %d per '
+                             'GPU, N=64000 @16kHz; gradients to amps, '
+                             'harmonic_distribution, noise_magnitudes' % B,
+                 'batch_per_gpu': B, 'global_batch': B * world,
+                 'step': 'ddsp_b200.autograd.decoder_train (DecoderFn) + '
+                         'losses.SpectralLoss (SpectralLossFn), eager autograd',
+                 'l2_policy': 'ring of 3 distinct input / target sets',
+                 'ffts': 'cuFFT through torch.fft (library call, not a hand kernel)'},
+      'e2e': {'value': world * B * N_SAMPLES / (ms_e2e * 1e-3), 'unit': 'samples/s',
+              'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d_bytes * world,
+              'd2h_bytes_per_step': 4 * world,
+              'api': 'pinned host network outputs + target -> device, decoder_train, '
+                     'SpectralLoss, backward; the loss value is read back'},
+      'gpu_launches': int(launches), 'clocks': clocks,
+      'roofline': {'bound': 'hbm', 'kernel': 'spectral_l1 (2048-point STFTs)',
+                   'achieved': l1_bytes / (ms_l1 * 1e-3) / 1e9, 'peak': peak,
+                   'unit': 'GB/s', 'frac': l1_bytes / (ms_l1 * 1e-3) / 1e9 / peak,
+                   'peak_source': peak_src + ' (MEASURED_PEAKS.json hbm_gbs)',
+                   'traffic': None, 'algorithmic_bytes_per_launch': l1_bytes,
+                   'kernel_ms': {'spectral_l1': ms_l1}},
+      'cpu_baseline': cpu,
+      'loss': float(last['loss'].detach()),
+  }
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return line
+
+
 def main():
   # Keep stdout clean for the ONE JSON line: NCCL (and anything else native)
   # writes its banners to fd 1, so run with fd 1 pointed at stderr and restore
@@ -694,8 +921,15 @@ def _main():
                   help='also time configs[1] / [0] / [3] on rank 0')
   ap.add_argument('--graph', type=int, default=1,
                   help='replay the step from a CUDA graph (0 = eager call)')
+  ap.add_argument('--config', default='decoder', choices=['decoder', 'c4'],
+                  help="'decoder' (default): configs[2] / configs[4]; 'c4': configs[3], "
+                       'forward + backward through SpectralLoss, batch 128 per GPU')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
+  if args.config == 'c4':
+    if args.steps == 50:
+      args.steps = 10
+    return run_c4_reference(args) if args.impl == 'reference' else run_c4(args)
   if args.impl == 'reference':
     return run_reference(args)
   return run_ours(args)

@@ -24,6 +24,8 @@ CTL_SCALE = 1
 CTL_NYQUIST = 2
 PAD_SAME = 0
 PAD_VALID = 1
+LTI_REVERSE_AUDIO = 1
+LTI_REVERSE_IR = 2
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers
 _i = ctypes.c_int
@@ -79,7 +81,7 @@ SIGNATURES = {
     'ddsp_b200_resample': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'ddsp_b200_fft_convolve_lti_workspace': (_sz, [_i, _i, _i, _i]),
     'ddsp_b200_fft_convolve_lti':
-        (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+        (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     'ddsp_b200_angular_cumsum':
         (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     'ddsp_b200_oscillator_bank_tf_sequential':
@@ -89,7 +91,8 @@ SIGNATURES = {
         (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
     'ddsp_b200_add': (_i, [_vp, _vp, _vp, _i64, _vp]),
     'ddsp_b200_frame_window': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    'ddsp_b200_frame_window_adjoint': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'ddsp_b200_frame_window_adjoint':
+        (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     'ddsp_b200_spectral_l1': (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _i, _i, _vp]),
 }
 

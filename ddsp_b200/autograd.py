@@ -147,6 +147,50 @@ class DecoderFn(torch.autograd.Function):
     return (d_amps, d_hd, d_f0, d_mags) + (None,) * 9
 
 
+class FftConvolveLtiFn(torch.autograd.Function):
+  """core.fft_convolve with one long impulse response per item (effects.Reverb,
+  effects.py:103-117), differentiable in both operands:
+    y[n]      = sum_s h[s] x[n + start - s]
+    dL/dx[m]  = (g * reverse(h)) [m + S - 1 - start]
+    dL/dh[s]  = (g * reverse(x)) [s + N - 1 - start]     (summed over the batch when
+                                                          the IR is shared)
+  - three calls of the same partitioned overlap-save kernels."""
+
+  @staticmethod
+  def forward(ctx, audio, ir, start, out_len):
+    audio = core.torch_float32(audio)
+    ir = core.torch_float32(ir)
+    ctx.save_for_backward(audio, ir)
+    ctx.cfg = (int(start), int(out_len))
+    return core.fft_convolve_lti(audio, ir, start, out_len)
+
+  @staticmethod
+  def backward(ctx, g):
+    audio, ir = ctx.saved_tensors
+    start, out_len = ctx.cfg
+    b, n = audio.shape
+    ir_batch, s = ir.shape
+    g = g.contiguous().to(torch.float32)
+    d_audio = d_ir = None
+    if ctx.needs_input_grad[0]:
+      off = s - 1 - start
+      if off >= 0:
+        d_audio = core.fft_convolve_lti(g, ir, off, n, reverse_ir=True)
+      else:      # crop starts beyond the IR length: shift through a padded gradient
+        gp = torch.nn.functional.pad(g, (-off, 0))
+        d_audio = core.fft_convolve_lti(gp, ir, 0, n, reverse_ir=True)
+    if ctx.needs_input_grad[1]:
+      off = n - 1 - start
+      if off >= 0:
+        d_ir = core.fft_convolve_lti(g, audio, off, s, reverse_ir=True)
+      else:
+        gp = torch.nn.functional.pad(g, (-off, 0))
+        d_ir = core.fft_convolve_lti(gp, audio, 0, s, reverse_ir=True)
+      if ir_batch == 1 and b > 1:
+        d_ir = d_ir.sum(0, keepdim=True)
+    return d_audio, d_ir, None, None
+
+
 class FilteredNoiseFn(torch.autograd.Function):
   """FilteredNoise.get_signal (synths.py:181-196), differentiable in magnitudes."""
 

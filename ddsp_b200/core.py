@@ -789,6 +789,30 @@ def _fft_convolve_cufft(audio, impulse_response, n_ir_frames, frame_size, fft_si
   return total[:, start:start + crop_size].contiguous()
 
 
+def fft_convolve_lti(audio, impulse_response, start, out_len, out=None,
+                     accumulate=False, reverse_audio=False, reverse_ir=False):
+  """Full linear convolution of audio [B, N] with ONE impulse response per item
+  [1 or B, S], cropped to [start, start + out_len): `ddsp_b200_fft_convolve_lti`
+  (partitioned overlap-save, hand-written FFTs).  reverse_*: read that operand back
+  to front (what the backward pass needs)."""
+  b, n = audio.shape
+  ir_batch, s_len = impulse_response.shape
+  if out is None:
+    out = torch.empty((b, out_len), dtype=torch.float32, device=audio.device)
+    accumulate = False
+  lib = _lib.load()
+  flags = ((_lib.LTI_REVERSE_AUDIO if reverse_audio else 0) |
+           (_lib.LTI_REVERSE_IR if reverse_ir else 0))
+  with _on_device_of(audio, impulse_response, out):
+    nbytes = lib.ddsp_b200_fft_convolve_lti_workspace(b, n, s_len, ir_batch)
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=audio.device)
+    _lib.check(lib.ddsp_b200_fft_convolve_lti(
+        _ptr(audio), _ptr(impulse_response), _ptr(out), b, n, s_len, ir_batch,
+        int(start), int(out_len), int(bool(accumulate)), flags, _ptr(ws), nbytes,
+        _stream()))
+  return out
+
+
 def fft_convolve(audio, impulse_response, padding: Text = 'same',
                  delay_compensation: int = -1, out=None, accumulate=False):
   """core.fft_convolve (core.py:1382-1473).
@@ -837,23 +861,23 @@ def fft_convolve(audio, impulse_response, padding: Text = 'same',
     # one long impulse response per item (effects.Reverb): hand-written
     # partitioned overlap-save convolution (csrc/longconv.cuh)
     ir2 = impulse_response.reshape(ir_batch, ir_size).contiguous()
-    if out is None:
-      out = torch.empty((batch_size, crop_size), dtype=torch.float32,
-                        device=audio.device)
-      accumulate = False
-    else:
+    if torch.is_grad_enabled() and (audio.requires_grad or ir2.requires_grad):
+      # trainable reverb (effects.py:70-79): forward and backward are the same
+      # kernels (the backward on time-reversed operands)
+      from ddsp_b200 import autograd as _ag
+      wet = _ag.FftConvolveLtiFn.apply(audio, ir2, int(start), int(crop_size))
+      if out is None:
+        return wet
       _check_out(out, (batch_size, crop_size), audio)
-    _no_grad_path('fft_convolve', audio, ir2)
-    lib = _lib.load()
-    with _on_device_of(audio, ir2, out):
-      nbytes = lib.ddsp_b200_fft_convolve_lti_workspace(batch_size, audio_size,
-                                                       ir_size, ir_batch)
-      ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=audio.device)
-      _lib.check(lib.ddsp_b200_fft_convolve_lti(
-          _ptr(audio), _ptr(ir2), _ptr(out), batch_size, audio_size, ir_size,
-          ir_batch, int(start), int(crop_size), int(bool(accumulate)), _ptr(ws),
-          nbytes, _stream()))
-    return out
+      if accumulate:
+        out += wet
+      else:
+        out.copy_(wet)
+      return out
+    if out is not None:
+      _check_out(out, (batch_size, crop_size), audio)
+    return fft_convolve_lti(audio, ir2, int(start), int(crop_size), out=out,
+                            accumulate=accumulate)
   if ir_size >= FFT_CONVOLVE_MIN_IR:
     # time-varying filter with long impulse responses (several IR frames of >= 2048
     # taps): no reference configuration does this; the reference's own framed

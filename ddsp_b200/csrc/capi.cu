@@ -850,7 +850,7 @@ size_t ddsp_b200_fft_convolve_lti_workspace(int B, int N, int S, int ir_batch) {
 
 int ddsp_b200_fft_convolve_lti(const float* audio, const float* impulse_response,
                                float* out, int B, int N, int S, int ir_batch,
-                               int start, int out_len, int accumulate,
+                               int start, int out_len, int accumulate, int flags,
                                void* workspace, size_t workspace_bytes, void* stream) {
   DDSP_REQUIRE(audio && impulse_response && out, DDSP_B200_E_INVALID,
                "fft_convolve_lti: null pointer");
@@ -877,17 +877,33 @@ int ddsp_b200_fft_convolve_lti(const float* audio, const float* impulse_response
   float2* H = Z + (size_t)B * g.n_in * lc::M;
   float2* W = H + (size_t)ir_batch * g.P * lc::M;
   cudaStream_t st = (cudaStream_t)stream;
-  lc::lc_fft_blocks<<<dim3(g.P, ir_batch), lc::THREADS, 0, st>>>(impulse_response, H, S,
-                                                                0, g.P, 1);
+  DDSP_REQUIRE((flags & ~3) == 0, DDSP_B200_E_INVALID,
+               "fft_convolve_lti: bad flags %d", flags);
+  lc::lc_fft_blocks<<<dim3(g.P, ir_batch), lc::THREADS, 0, st>>>(
+      impulse_response, H, S, 0, g.P, 1, (flags & DDSP_B200_LTI_REVERSE_IR) ? 1 : 0);
   DDSP_CHECK_LAUNCH("fft_convolve_lti(ir spectra)");
-  lc::lc_fft_blocks<<<dim3(g.n_in, B), lc::THREADS, 0, st>>>(audio, Z, N, g.n2, g.n_in, 0);
+  lc::lc_fft_blocks<<<dim3(g.n_in, B), lc::THREADS, 0, st>>>(
+      audio, Z, N, g.n2, g.n_in, 0, (flags & DDSP_B200_LTI_REVERSE_AUDIO) ? 1 : 0);
   DDSP_CHECK_LAUNCH("fft_convolve_lti(audio spectra)");
-  lc::lc_mac_ifft<<<dim3(g.n_out, B), lc::THREADS, 0, st>>>(
-      Z, H, W, g.n_in, g.P, g.n_out, ir_batch == 1 ? 0 : g.P * lc::M);
+  // w blocks the crop reads: positions [start, start + out_len) through the real
+  // half and [start - n2, start + out_len - n2) through the imaginary half
+  const int lo_pos = std::max(0, start - g.n2);
+  const int hi_pos = std::min(g.w_len, start + out_len);      // exclusive
+  const int j_first = lo_pos / lc::L;
+  const int j_last = std::min(g.n_out - 1, (hi_pos - 1) / lc::L);
+  const int n_blocks = j_last - j_first + 1;
+  {
+    int rc = set_smem(lc::lc_mac_ifft, lc::kMacSmem, "fft_convolve_lti");
+    if (rc) return rc;
+  }
+  lc::lc_mac_ifft<<<dim3((n_blocks + lc::JT - 1) / lc::JT, B), lc::THREADS, lc::kMacSmem,
+                    st>>>(
+      Z, H, W, g.n_in, g.P, g.n_out, ir_batch == 1 ? 0 : g.P * lc::M, j_first, n_blocks);
   DDSP_CHECK_LAUNCH("fft_convolve_lti(multiply-accumulate + inverse)");
   const int cgrid = std::min((out_len + 255) / 256, 8 * kNumSMs);
   lc::lc_combine<<<dim3(cgrid, B), 256, 0, st>>>(W, out, g.n2, g.w_len, start, out_len,
-                                               N + S - 1, accumulate);
+                                               N + S - 1, accumulate, j_first * lc::L,
+                                               (j_last + 1) * lc::L);
   DDSP_CHECK_LAUNCH("fft_convolve_lti(combine)");
   return 0;
 }
@@ -1089,7 +1105,9 @@ int ddsp_b200_frame_window(const float* audio, const float* window, float* frame
 
 int ddsp_b200_frame_window_adjoint(const float* grad_frames, const float* window,
                                    float* grad_audio, int B, int N, int n_frames,
-                                   int frame_size, int frame_step, void* stream) {
+                                   int frame_size, int frame_step,
+                                   const float* scale_device, int accumulate,
+                                   void* stream) {
   DDSP_REQUIRE(grad_frames && window && grad_audio, DDSP_B200_E_INVALID,
                "frame_window_adjoint: null pointer");
   DDSP_REQUIRE(B >= 0 && N >= 1 && n_frames >= 1 && frame_size >= 1 && frame_step >= 1 &&
@@ -1098,7 +1116,8 @@ int ddsp_b200_frame_window_adjoint(const float* grad_frames, const float* window
   if (B == 0) return 0;
   dim3 grid((N + 255) / 256, B);
   frame_window_adjoint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      grad_frames, window, grad_audio, N, n_frames, frame_size, frame_step);
+      grad_frames, window, grad_audio, N, n_frames, frame_size, frame_step,
+      scale_device, accumulate);
   DDSP_CHECK_LAUNCH("frame_window_adjoint");
   return 0;
 }

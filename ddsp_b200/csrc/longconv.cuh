@@ -17,7 +17,10 @@
 //     IFFT(sum_p Z_{j-p} H_p).
 // Kernels: lc_fft_blocks (windows of z, or partitions of h -> spectra),
 // lc_mac_ifft (spectral multiply-accumulate over the partitions + inverse FFT ->
-// w blocks), lc_combine (Re / Im recombination, delay crop, optional accumulate).
+// w blocks; four output blocks per CTA, windows sliding through registers; only
+// the blocks the crop needs are produced), lc_combine (Re / Im recombination, delay
+// crop, optional accumulate).  The backward pass (d audio, d impulse response) is
+// the same three kernels on time-reversed operands (`reverse` flag).
 #pragma once
 #include "common.cuh"
 
@@ -79,10 +82,11 @@ __device__ __forceinline__ void ifft_dit(float2* s, const float2* tw, int tid) {
 
 // mode 0: window j of z (two time-halves of audio item b packed as re / im);
 // mode 1: partition p of the impulse response of item b (real, zero-padded).
-// grid (n_blocks, items).
+// reverse: the source is read back to front (x[len - 1 - n]) - the backward pass
+// convolves with time-reversed signals.  grid (n_blocks, items).
 __global__ void __launch_bounds__(THREADS)
 lc_fft_blocks(const float* __restrict__ src, float2* __restrict__ spec, int len,
-              int n2, int n_blocks, int mode) {
+              int n2, int n_blocks, int mode, int reverse) {
   __shared__ float2 s[M];
   __shared__ float2 tw[M / 2];
   const int tid = threadIdx.x, j = blockIdx.x, b = blockIdx.y;
@@ -93,12 +97,12 @@ lc_fft_blocks(const float* __restrict__ src, float2* __restrict__ spec, int len,
     if (mode == 0) {
       const long long n = (long long)(j - 1) * L + i;          // index into z
       if (n >= 0 && n < n2) {
-        re = x[n];
-        if (n + n2 < len) im = x[n + n2];
+        re = x[reverse ? len - 1 - n : n];
+        if (n + n2 < len) im = x[reverse ? len - 1 - (n + n2) : n + n2];
       }
     } else if (i < L) {
       const long long n = (long long)j * L + i;
-      if (n < len) re = x[n];
+      if (n < len) re = x[reverse ? len - 1 - n : n];
     }
     s[i] = make_float2(re, im);
   }
@@ -107,40 +111,93 @@ lc_fft_blocks(const float* __restrict__ src, float2* __restrict__ spec, int len,
   for (int i = tid; i < M; i += THREADS) out[i] = s[i];
 }
 
-// w block j of item b: IFFT(sum_p Z[b, j - p] H[bi, p]) -> last L samples.
-// grid (n_out_blocks, B).  Z: [B, n_in, M], H: [Bi, P, M], W: [B, n_out * L].
-__global__ void __launch_bounds__(THREADS)
+// w blocks j0 .. j0 + JT - 1 of item b: block j = last L samples of
+// IFFT(sum_p Z[b, j - p] H[bi, p]).  One CTA owns JT consecutive output blocks and
+// walks the partitions once: per partition ONE spectrum of H and ONE new window of
+// Z are loaded (the other JT - 1 windows slide through registers), so the L2
+// traffic per output block is 2 P / JT spectra instead of 2 P.
+// grid (ceil(n_blocks / JT), B); blocks j_first + [0, n_blocks) are produced.
+// Z: [B, n_in, M], H: [Bi, P, M], W: [B, n_out * L].
+constexpr int JT = 4;
+constexpr int EPT = 4;                  // spectrum elements per thread per pass
+constexpr int PASSES = M / (THREADS * EPT);
+constexpr size_t kMacSmem = sizeof(float2) * ((size_t)JT * M + M / 2);
+
+__global__ void __launch_bounds__(THREADS, 2)
 lc_mac_ifft(const float2* __restrict__ Z, const float2* __restrict__ H,
-            float2* __restrict__ W, int n_in, int P, int n_out, int ir_batch_stride) {
-  __shared__ float2 s[M];
-  __shared__ float2 tw[M / 2];
-  const int tid = threadIdx.x, j = blockIdx.x, b = blockIdx.y;
+            float2* __restrict__ W, int n_in, int P, int n_out, int ir_batch_stride,
+            int j_first, int n_blocks) {
+  extern __shared__ __align__(16) unsigned char lc_smem[];
+  float2* sAcc = reinterpret_cast<float2*>(lc_smem);            // [JT][M]
+  float2* tw = sAcc + (size_t)JT * M;                           // [M / 2]
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const int j0 = j_first + blockIdx.x * JT;
+  const int jt_n = min(JT, j_first + n_blocks - j0);
   fill_twiddles(tw, tid);
-  float2 acc[M / THREADS];
-#pragma unroll
-  for (int e = 0; e < M / THREADS; ++e) acc[e] = make_float2(0.f, 0.f);
   const float2* Zb = Z + (size_t)b * n_in * M;
   const float2* Hb = H + (size_t)b * ir_batch_stride;
-  const int p_lo = max(0, j - (n_in - 1)), p_hi = min(P - 1, j);
-  for (int p = p_lo; p <= p_hi; ++p) {
-    const float2* zp = Zb + (size_t)(j - p) * M;
-    const float2* hp = Hb + (size_t)p * M;
+  // partitions that reach any block of the tile: window j0 + k - p in [0, n_in)
+  const int p_lo = max(0, j0 - (n_in - 1)), p_hi = min(P - 1, j0 + JT - 1);
+#pragma unroll 1
+  for (int pass = 0; pass < PASSES; ++pass) {       // the spectrum in two halves
+    const int f0 = pass * THREADS * EPT + tid;
+    float2 acc[JT][EPT], zw[JT][EPT];
 #pragma unroll
-    for (int e = 0; e < M / THREADS; ++e) {
-      const int f = tid + e * THREADS;
-      const float2 z = zp[f], h = hp[f];
-      acc[e].x = fmaf(z.x, h.x, fmaf(-z.y, h.y, acc[e].x));
-      acc[e].y = fmaf(z.x, h.y, fmaf(z.y, h.x, acc[e].y));
+    for (int k = 0; k < JT; ++k)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) acc[k][e] = make_float2(0.f, 0.f);
+    auto load_window = [&](int w, float2 (&dst)[EPT]) {
+      if (w >= 0 && w < n_in) {
+        const float2* zp = Zb + (size_t)w * M + f0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) dst[e] = zp[e * THREADS];
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) dst[e] = make_float2(0.f, 0.f);
+      }
+    };
+    // slot convention: at partition p = p_lo + u (u mod JT), window j0 + k - p sits
+    // in zw[(k - u) & (JT - 1)]
+#pragma unroll
+    for (int k = 0; k < JT; ++k) load_window(j0 + k - p_lo, zw[k]);
+    for (int pb = p_lo; pb <= p_hi; pb += JT) {
+#pragma unroll
+      for (int u = 0; u < JT; ++u) {
+        const int p = pb + u;
+        if (p <= p_hi) {
+          const float2* hp = Hb + (size_t)p * M + f0;
+          float2 h[EPT];
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) h[e] = hp[e * THREADS];
+#pragma unroll
+          for (int k = 0; k < JT; ++k) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+              const float2 z = zw[(k - u) & (JT - 1)][e];
+              acc[k][e].x = fmaf(z.x, h[e].x, fmaf(-z.y, h[e].y, acc[k][e].x));
+              acc[k][e].y = fmaf(z.x, h[e].y, fmaf(z.y, h[e].x, acc[k][e].y));
+            }
+          }
+          // next partition: windows shift down by one; the slot of the highest
+          // window (k = JT - 1) is refilled with window j0 - (p + 1)
+          load_window(j0 - (p + 1), zw[(JT - 1 - u) & (JT - 1)]);
+        }
+      }
     }
-  }
 #pragma unroll
-  for (int e = 0; e < M / THREADS; ++e) s[tid + e * THREADS] = acc[e];
-  ifft_dit(s, tw, tid);
+    for (int k = 0; k < JT; ++k)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) sAcc[(size_t)k * M + f0 + e * THREADS] = acc[k][e];
+  }
   const float scale = 1.0f / (float)M;
-  float2* out = W + ((size_t)b * n_out + j) * L;
-  for (int i = tid; i < L; i += THREADS) {
-    const float2 v = s[L + i];
-    out[i] = make_float2(v.x * scale, v.y * scale);
+  for (int k = 0; k < jt_n; ++k) {
+    float2* s = sAcc + (size_t)k * M;
+    ifft_dit(s, tw, tid);
+    float2* out = W + ((size_t)b * n_out + (j0 + k)) * L;
+    for (int i = tid; i < L; i += THREADS) {
+      const float2 v = s[L + i];
+      out[i] = make_float2(v.x * scale, v.y * scale);
+    }
   }
 }
 
@@ -148,7 +205,7 @@ lc_mac_ifft(const float2* __restrict__ Z, const float2* __restrict__ H,
 // crop_and_compensate_delay, core.py:1338-1379).  w is valid on [0, n_out * L).
 __global__ void __launch_bounds__(256)
 lc_combine(const float2* __restrict__ W, float* __restrict__ out, int n2, int w_len,
-           int start, int out_len, int total_len, int accumulate) {
+           int start, int out_len, int total_len, int accumulate, int w_lo, int w_hi) {
   const int b = blockIdx.y;
   const float2* w = W + (size_t)b * w_len;
   float* o = out + (size_t)b * out_len;
@@ -157,9 +214,11 @@ lc_combine(const float2* __restrict__ W, float* __restrict__ out, int n2, int w_
     const int t = n + start;                   // position in the full convolution
     float v = 0.f;
     if (t < total_len) {
-      if (t < w_len) v = w[t].x;
+      // only [w_lo, w_hi) was produced; w is identically zero outside the blocks
+      // that any partition reaches
+      if (t >= w_lo && t < w_hi) v = w[t].x;
       const int u = t - n2;
-      if (u >= 0 && u < w_len) v += w[u].y;
+      if (u >= w_lo && u < w_hi) v += w[u].y;
     }
     if (accumulate) v += o[n];
     o[n] = v;

@@ -29,11 +29,15 @@ frame_window_kernel(const float* __restrict__ audio, const float* __restrict__ w
   *reinterpret_cast<float4*>(frames + ((size_t)b * T) * n + e) = v;
 }
 
-// grad_audio[b, s] = sum_t window[s - t step] * grad_frames[b, t, s - t step]
+// grad_audio[b, s] (+)= scale * sum_t window[s - t step] * grad_frames[b, t, s - t step]
+// scale_ptr: optional DEVICE scalar (the upstream gradient of the loss value), so
+// the six FFT sizes of the multi-scale loss accumulate into one buffer without a
+// host round trip or an elementwise pass.
 __global__ void __launch_bounds__(256)
 frame_window_adjoint_kernel(const float* __restrict__ gframes,
                             const float* __restrict__ window,
-                            float* __restrict__ gaudio, int N, int T, int n, int step) {
+                            float* __restrict__ gaudio, int N, int T, int n, int step,
+                            const float* __restrict__ scale_ptr, int accumulate) {
   const int b = blockIdx.y;
   const int s = blockIdx.x * 256 + threadIdx.x;
   if (s >= N) return;
@@ -47,7 +51,10 @@ frame_window_adjoint_kernel(const float* __restrict__ gframes,
     const int i = s - t * step;
     if (i >= 0 && i < n) acc = fmaf(window[i], g[(size_t)t * n + i], acc);
   }
-  gaudio[(size_t)b * N + s] = acc;
+  if (scale_ptr != nullptr) acc *= *scale_ptr;
+  float* o = gaudio + (size_t)b * N + s;
+  if (accumulate) acc += *o;
+  *o = acc;
 }
 
 // One pass over the two complex STFTs: sums of |mag_t - mag_a| and

@@ -76,16 +76,9 @@ class SpectralLoss:
                     for sz in self.fft_sizes))
 
   def _call_fused(self, target_audio, audio):
-    loss = 0.0
-    with torch.no_grad():
-      target = target_audio.to(torch.float32)
-    for size in self.fft_sizes:
-      with torch.no_grad():
-        stft_t = spectral_ops.stft_cuda(target, size)
-      loss = loss + spectral_ops.SpectralTermFn.apply(
-          stft_t, audio, int(size), int(size * 0.25), max(self.mag_weight, 0.0),
-          max(self.logmag_weight, 0.0))
-    return loss
+    return spectral_ops.SpectralLossFn.apply(
+        target_audio.detach(), audio, tuple(int(s) for s in self.fft_sizes),
+        max(self.mag_weight, 0.0), max(self.logmag_weight, 0.0))
 
   def call(self, target_audio, audio, weights=None):
     if self._fusable(target_audio, audio, weights):

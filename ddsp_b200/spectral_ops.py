@@ -85,7 +85,7 @@ class FrameWindowFn(torch.autograd.Function):
     grad_audio = torch.empty((b, n), dtype=torch.float32, device=grad_frames.device)
     _lib.check(_lib.load().ddsp_b200_frame_window_adjoint(
         grad_frames.data_ptr(), _hann(frame_size, grad_frames.device).data_ptr(),
-        grad_audio.data_ptr(), b, n, n_frames, frame_size, step, _stream()))
+        grad_audio.data_ptr(), b, n, n_frames, frame_size, step, None, 0, _stream()))
     return grad_audio, None, None
 
 
@@ -144,8 +144,68 @@ class SpectralTermFn(torch.autograd.Function):
     grad_audio = torch.empty((b, n), dtype=torch.float32, device=grad.device)
     _lib.check(_lib.load().ddsp_b200_frame_window_adjoint(
         grad_frames.data_ptr(), _hann(frame_size, grad.device).data_ptr(),
-        grad_audio.data_ptr(), b, n, n_frames, frame_size, step, _stream()))
+        grad_audio.data_ptr(), b, n, n_frames, frame_size, step, None, 0, _stream()))
     return None, grad_audio * grad_out, None, None, None, None
+
+
+_LOSS_WEIGHTS = {}
+
+
+class SpectralLossFn(torch.autograd.Function):
+  """The whole multi-scale 'L1' spectrogram loss (losses.SpectralLoss.call,
+  losses.py:194-243, `ae.gin` weights) as ONE autograd node: per FFT size framing +
+  Hann (kernel), cuFFT r2c of target and value, one pass leaving both L1 sums and
+  the value-STFT gradient IN PLACE of the value STFT; backward is cuFFT c2r plus a
+  windowed overlap-add per size that accumulates, already scaled by the upstream
+  gradient (read on the device), into a single dL/d audio buffer.  No elementwise
+  torch op on either pass."""
+
+  @staticmethod
+  def forward(ctx, target, audio, fft_sizes, mag_weight, logmag_weight):
+    from ddsp_b200 import _lib
+    lib = _lib.load()
+    audio = audio.to(torch.float32).contiguous()
+    target = target.to(torch.float32).contiguous()
+    b, n = audio.shape
+    sums = torch.zeros((len(fft_sizes), 2), dtype=torch.float64, device=audio.device)
+    grads, counts = [], []
+    for idx, size in enumerate(fft_sizes):
+      size = int(size)
+      step = int(size * 0.25)
+      xt = torch.fft.rfft(_frame_window(target, size, step), n=size, dim=-1)
+      xv = torch.fft.rfft(_frame_window(audio, size, step), n=size, dim=-1)
+      m = xv.numel()
+      _lib.check(lib.ddsp_b200_spectral_l1(
+          xt.data_ptr(), xv.data_ptr(), xv.data_ptr(), sums[idx].data_ptr(), m,
+          float(mag_weight), float(logmag_weight), xv.shape[-1], size, _stream()))
+      del xt
+      grads.append(xv)                   # now holds d loss_size / d X_value, irfft-ready
+      counts.append(m)
+    key = (tuple(counts), float(mag_weight), float(logmag_weight), str(audio.device))
+    if key not in _LOSS_WEIGHTS:
+      _LOSS_WEIGHTS[key] = torch.tensor(
+          [[mag_weight / m, logmag_weight / m] for m in counts], dtype=torch.float64,
+          device=audio.device)
+    ctx.save_for_backward(*grads)
+    ctx.meta = (b, n, tuple(int(sz) for sz in fft_sizes))
+    return (sums * _LOSS_WEIGHTS[key]).sum().to(torch.float32)
+
+  @staticmethod
+  def backward(ctx, grad_out):
+    from ddsp_b200 import _lib
+    lib = _lib.load()
+    b, n, sizes = ctx.meta
+    grads = ctx.saved_tensors
+    go = grad_out.to(torch.float32).contiguous()
+    grad_audio = torch.empty((b, n), dtype=torch.float32, device=go.device)
+    for idx, size in enumerate(sizes):
+      step = int(size * 0.25)
+      n_frames = -(-n // step)
+      gf = torch.fft.irfft(grads[idx], n=size, dim=-1).contiguous()
+      _lib.check(lib.ddsp_b200_frame_window_adjoint(
+          gf.data_ptr(), _hann(size, go.device).data_ptr(), grad_audio.data_ptr(), b, n,
+          n_frames, size, step, go.data_ptr(), int(idx > 0), _stream()))
+    return None, grad_audio, None, None, None
 
 
 def stft_cuda(audio, frame_size, overlap=0.75):

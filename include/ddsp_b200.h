@@ -259,11 +259,15 @@ int ddsp_b200_oscillator_bank(const float* frequency_envelopes,
  * FFTs.  audio [B,N], impulse_response [ir_batch (1 or B), S] -> out [B,out_len] =
  * full convolution [start, start + out_len) (crop_and_compensate_delay,
  * core.py:1338-1379; start + out_len <= N + S - 1).  workspace:
- * ddsp_b200_fft_convolve_lti_workspace(B, N, S, ir_batch) bytes. */
+ * ddsp_b200_fft_convolve_lti_workspace(B, N, S, ir_batch) bytes.
+ * flags: DDSP_B200_LTI_REVERSE_AUDIO / _IR read that operand back to front - the
+ * backward pass is the same convolution on time-reversed signals:
+ *   d audio = (g * reverse(ir)) [S-1-start, +N),  d ir = (g * reverse(audio)) [N-1-start, +S). */
+enum { DDSP_B200_LTI_REVERSE_AUDIO = 1, DDSP_B200_LTI_REVERSE_IR = 2 };
 size_t ddsp_b200_fft_convolve_lti_workspace(int B, int N, int S, int ir_batch);
 int ddsp_b200_fft_convolve_lti(const float* audio, const float* impulse_response,
                                float* out, int B, int N, int S, int ir_batch,
-                               int start, int out_len, int accumulate,
+                               int start, int out_len, int accumulate, int flags,
                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* core.angular_cumsum (core.py:799-866) and tf.cumsum (core.py:955) on
@@ -313,7 +317,9 @@ int ddsp_b200_resample(const float* in, float* out, int B, int F, int C, int N,
  * frame_window: tf.signal.stft's framing + periodic Hann window with pad_end=True
  * (spectral_ops.py:34-47): audio [B,N] -> frames [B, n_frames, frame_size],
  * frames[b,t,i] = window[i] * audio[b, t*frame_step + i] (0 past the end).
- * frame_window_adjoint: its transpose, grad_frames -> grad_audio [B,N].
+ * frame_window_adjoint: its transpose, grad_frames -> grad_audio [B,N], times the
+ * optional DEVICE scalar *scale_device (NULL = 1), added to grad_audio when
+ * accumulate != 0 (the FFT sizes of the multi-scale loss share one buffer).
  * spectral_l1: for complex STFTs [n_bins_total] (interleaved re/im) of target and
  * value: sums[0] += sum |mag_t - mag_v|, sums[1] += sum |safe_log mag_t -
  * safe_log mag_v| (core.py:213-216), and grad_value = d/dX_v of
@@ -327,7 +333,9 @@ int ddsp_b200_frame_window(const float* audio, const float* window, float* frame
                            void* stream);
 int ddsp_b200_frame_window_adjoint(const float* grad_frames, const float* window,
                                    float* grad_audio, int B, int N, int n_frames,
-                                   int frame_size, int frame_step, void* stream);
+                                   int frame_size, int frame_step,
+                                   const float* scale_device, int accumulate,
+                                   void* stream);
 int ddsp_b200_spectral_l1(const float* stft_target, const float* stft_value,
                           float* grad_value, double* sums, int64_t n_bins_total,
                           float mag_weight, float logmag_weight, int n_bins,

@@ -127,3 +127,40 @@ def decoder(amps, hd, f0, mags, n_samples=64000, sample_rate=16000,
   harm = harmonic_signal(a, h, f0, n_samples, sample_rate)
   nz = noise_signal(noise_controls(mags), n_samples, window_size, noise)
   return nz + harm
+
+
+def spectral_loss(target, audio, fft_sizes=(2048, 1024, 512, 256, 128, 64),
+                  mag_weight=1.0, logmag_weight=1.0):
+  """losses.SpectralLoss.call with loss_type='L1' (losses.py:194-243) on
+  spectral_ops.compute_mag (spectral_ops.py:34-70): tf.signal.stft(pad_end=True),
+  periodic Hann, frame_step = size / 4 - op by op in float32 torch-CPU ops."""
+  loss = 0.0
+  n = audio.shape[-1]
+  for size in fft_sizes:
+    step = size // 4
+    n_frames = -(-n // step)
+    pad = (n_frames - 1) * step + size - n
+    win = torch.hann_window(size, periodic=True, dtype=F32)
+
+    def mag(x):
+      fr = torch.nn.functional.pad(x, (0, pad)).unfold(-1, size, step)
+      return torch.abs(torch.fft.rfft(fr * win, dim=-1))
+
+    t, v = mag(target), mag(audio)
+    if mag_weight > 0:
+      loss = loss + mag_weight * torch.mean(torch.abs(t - v))
+    if logmag_weight > 0:
+      slog = lambda m: torch.log(torch.where(m <= 0.0, torch.full_like(m, 1e-5), m))
+      loss = loss + logmag_weight * torch.mean(torch.abs(slog(t) - slog(v)))
+  return loss
+
+
+def train_step(amps, hd, f0, mags, target, noise=None, n_samples=64000):
+  """configs[3] on the CPU: decoder forward from raw network outputs, multi-scale
+  SpectralLoss, backward to the three raw inputs (torch autograd standing in for
+  TF's).  Returns the loss value."""
+  leaves = [t.detach().clone().requires_grad_(True) for t in (amps, hd, mags)]
+  audio = decoder(leaves[0], leaves[1], f0, leaves[2], n_samples=n_samples, noise=noise)
+  loss = spectral_loss(target, audio)
+  loss.backward()
+  return float(loss)

@@ -99,9 +99,9 @@ def test_trainable_reverb_and_fir_filter():
     (2, 64000, 48000, 2, 'same', 0),        # effects.Reverb at the ae.gin length
     (3, 64000, 48000, 1, 'same', 0),        # one trainable IR shared by the batch
     (2, 16000, 2048, 2, 'same', -1),        # smallest IR on this route, auto delay
-    (2, 5000, 9000, 2, 'valid', -1),        # IR longer than the audio, full tail
+    (2, 5000, 9000, 2, 'valid', 0),         # IR longer than the audio, full tail
     (1, 1023, 2049, 1, 'same', 0),          # ragged against the 1024-sample blocks
-    (2, 4097, 4096, 2, 'valid', 5)])
+    (2, 4097, 4096, 2, 'same', 5)])
 def test_long_impulse_response_convolution_kernel(B, n, taps, ir_batch, padding, delay):
   """`ddsp_b200_fft_convolve_lti` (partitioned overlap-save, hand-written FFTs)
   behind core.fft_convolve for 2-D / single-frame impulse responses >= 2048 taps,
@@ -122,3 +122,28 @@ def test_long_impulse_response_convolution_kernel(B, n, taps, ir_batch, padding,
   acc = core.fft_convolve(audio, ir, padding=padding, delay_compensation=delay,
                           out=base.clone(), accumulate=True)
   assert float((acc - (got + 0.25)).abs().max()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shared', [True, False])
+def test_long_convolution_backward_matches_autograd(shared):
+  """FftConvolveLtiFn (the trainable Reverb): d audio and d impulse response from
+  the same kernels on reversed operands, against float64 autograd of torch.fft."""
+  from ddsp_b200 import autograd as ag
+  torch.manual_seed(3)
+  B, n, taps, start = 3, 6000, 5000, 0
+  audio = torch.randn(B, n, device='cuda')
+  ir = torch.randn(1 if shared else B, taps, device='cuda') * 0.02
+  g = torch.randn(B, n, device='cuda')
+  a1, h1 = audio.clone().requires_grad_(True), ir.clone().requires_grad_(True)
+  y = core.fft_convolve(a1, h1, padding='same', delay_compensation=start)
+  (y * g).sum().backward()
+  a2, h2 = audio.double().requires_grad_(True), ir.double().requires_grad_(True)
+  m = n + taps - 1
+  yr = torch.fft.irfft(torch.fft.rfft(a2, m) * torch.fft.rfft(h2.expand(B, taps), m), m)
+  yr = yr[:, start:start + n]
+  (yr * g.double()).sum().backward()
+  assert float((y.double() - yr).abs().max() / yr.abs().max()) < 1e-4
+  for got, want in ((a1.grad, a2.grad), (h1.grad, h2.grad)):
+    err = float((got.double() - want).abs().max() / want.abs().max())
+    assert err < 2e-4, err
