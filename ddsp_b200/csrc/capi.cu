@@ -17,6 +17,7 @@
 #include "noise_pipe.cuh"
 #include "host_pipeline.cuh"
 #include "backward.cuh"
+#include "harmonic_bwd2.cuh"
 #include "controls_bwd.cuh"
 #include "oscbank.cuh"
 #include "sinusoidal.cuh"
@@ -638,6 +639,12 @@ int ddsp_b200_harmonic_backward(const float* f0_hz, const float* grad_audio,
                DDSP_B200_E_UNSUPPORTED,
                "harmonic_backward: needs hop %% 64 == 0 (hop = %d)", p.hop);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool use_v1 = [] {
+    const char* e = getenv("DDSP_B200_HARM_BWD");
+    return e != nullptr && strcmp(e, "v1") == 0;
+  }();
+  if (!use_v1 && harmonic_backward2_supported(p))
+    return launch_harmonic_backward2(p, grad_audio, g0, g1, st);
   const size_t gbytes = sizeof(float) * (size_t)B * F * K;
   DDSP_CUDA_TRY(cudaMemsetAsync(g0, 0, gbytes, st), "harmonic_backward: memset g0");
   DDSP_CUDA_TRY(cudaMemsetAsync(g1, 0, gbytes, st), "harmonic_backward: memset g1");
@@ -1129,7 +1136,7 @@ int ddsp_b200_spectral_l1(const float* stft_target, const float* stft_value,
   DDSP_REQUIRE(stft_target && stft_value && grad_value && sums, DDSP_B200_E_INVALID,
                "spectral_l1: null pointer");
   DDSP_REQUIRE(n_bins_total >= 1 && n_bins >= 1 && n_bins_total % n_bins == 0 &&
-                   (irfft_size == 0 || irfft_size == 2 * (n_bins - 1)),
+                   (irfft_size == 0 || irfft_size == -1 || irfft_size == 2 * (n_bins - 1)),
                DDSP_B200_E_INVALID, "spectral_l1: bad sizes (total %lld, bins %d, irfft %d)",
                (long long)n_bins_total, n_bins, irfft_size);
   DDSP_REQUIRE((((uintptr_t)stft_target | (uintptr_t)stft_value | (uintptr_t)grad_value) & 15) == 0,

@@ -102,8 +102,11 @@ spectral_l1_kernel(const float2* __restrict__ xt, const float2* __restrict__ xa,
       if (irfft_scale) {
         // pre-scale for the transpose of rfft written as a plain irfft:
         // d/dx = n * irfft(Y), Y = G at DC / Nyquist, G / 2 in between
+        // irfft_scale = -1: the caller's inverse transform is unnormalised
+        // (norm='forward'), so only the halving of the interior bins remains
         const int k = (int)((e + h) % n_bins);
-        dma *= (k == 0 || k == n_bins - 1) ? (float)irfft_scale : 0.5f * (float)irfft_scale;
+        const float sc = irfft_scale < 0 ? 1.0f : (float)irfft_scale;
+        dma *= (k == 0 || k == n_bins - 1) ? sc : 0.5f * sc;
       }
       g[2 * h] = dma * ar;
       g[2 * h + 1] = dma * ai;

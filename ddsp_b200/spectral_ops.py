@@ -177,7 +177,7 @@ class SpectralLossFn(torch.autograd.Function):
       m = xv.numel()
       _lib.check(lib.ddsp_b200_spectral_l1(
           xt.data_ptr(), xv.data_ptr(), xv.data_ptr(), sums[idx].data_ptr(), m,
-          float(mag_weight), float(logmag_weight), xv.shape[-1], size, _stream()))
+          float(mag_weight), float(logmag_weight), xv.shape[-1], -1, _stream()))
       del xt
       grads.append(xv)                   # now holds d loss_size / d X_value, irfft-ready
       counts.append(m)
@@ -201,7 +201,9 @@ class SpectralLossFn(torch.autograd.Function):
     for idx, size in enumerate(sizes):
       step = int(size * 0.25)
       n_frames = -(-n // step)
-      gf = torch.fft.irfft(grads[idx], n=size, dim=-1).contiguous()
+      # unnormalised inverse (the 1/n pass would be an elementwise kernel over the
+      # frames; spectral_l1 left the spectrum scaled for exactly this)
+      gf = torch.fft.irfft(grads[idx], n=size, dim=-1, norm='forward').contiguous()
       _lib.check(lib.ddsp_b200_frame_window_adjoint(
           gf.data_ptr(), _hann(size, go.device).data_ptr(), grad_audio.data_ptr(), b, n,
           n_frames, size, step, go.data_ptr(), int(idx > 0), _stream()))

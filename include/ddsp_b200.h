@@ -326,7 +326,8 @@ int ddsp_b200_resample(const float* in, float* out, int B, int F, int C, int N,
  * mag_weight * mean|.| + logmag_weight * mean|.| (losses.py:102-127, 'L1').
  * n_bins = bins per frame.  irfft_size = 0: grad_value is the plain gradient;
  * irfft_size = 2 (n_bins - 1): it is pre-scaled so that irfft(grad_value,
- * irfft_size) is the gradient w.r.t. the real frames (the transpose of rfft).
+ * irfft_size) is the gradient w.r.t. the real frames (the transpose of rfft);
+ * irfft_size = -1: the same for an UNNORMALISED inverse transform (no 1/n pass).
  * sums must be zeroed by the caller. */
 int ddsp_b200_frame_window(const float* audio, const float* window, float* frames,
                            int B, int N, int n_frames, int frame_size, int frame_step,
