@@ -798,6 +798,38 @@ def run_c4(args):
   launches = (lib.ddsp_b200_launch_count() - c0) * args.steps // (args.steps + args.warmup)
   value = world * B * N_SAMPLES / (ms_step * 1e-3)
 
+  # the same step replayed from CUDA graphs (whole forward + backward captured, one
+  # graph per input set; each graph keeps the Philox offset it was captured with, so
+  # the noise repeats every len(sets) steps - reported next to the eager number, not
+  # instead of it): what is left when the 64 launches cost no host time
+  ms_graph, graph_err = None, None
+  try:
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      for i in range(len(sets)):
+        step(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graphs = []
+    for i, d in enumerate(sets):
+      for k in grad_keys:
+        d[k].grad = None
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g, stream=side):
+        audio = ag.decoder_train(d['amps'], d['harmonic_distribution'], d['f0_hz'],
+                                 d['noise_magnitudes'], n_samples=N_SAMPLES,
+                                 window_size=0, seed=1 + rank, offset=1000 + i)
+        loss_obj(d['target'], audio).backward()
+      graphs.append(g)
+    torch.cuda.synchronize()
+    ms_graph = timed(lambda i: graphs[i % len(graphs)].replay(), args.steps,
+                     args.warmup) / args.steps
+    del graphs
+  except Exception as e:  # pylint: disable=broad-except
+    graph_err = repr(e)[:300]
+    torch.cuda.synchronize()
+
   # e2e: host network outputs + target in, loss value out (gradients stay on the GPU)
   loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
@@ -882,6 +914,9 @@ def run_c4(args):
                    'kernel_ms': {'spectral_l1': ms_l1}},
       'cpu_baseline': cpu,
       'loss': float(last['loss'].detach()),
+      'ms_per_step_graph_replay': ms_graph,
+      'graph_replay_note': graph_err or ('whole fwd+bwd step captured per input set; '
+                                         'Philox offset fixed per graph'),
   }
   if world > 1:
     dist.barrier()

@@ -22,7 +22,7 @@ def _newest_mtime():
   newest = 0.0
   for root in (CSRC, os.path.join(_HERE, '..', 'include')):
     for name in os.listdir(root):
-      if name.endswith(('.cu', '.cuh', '.h')):
+      if name.endswith(('.cu', '.cuh', '.h', '.inc')):
         newest = max(newest, os.path.getmtime(os.path.join(root, name)))
   return newest
 

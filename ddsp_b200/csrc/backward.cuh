@@ -18,13 +18,13 @@
 // magnitudes:  dL/dh_j[m] = sum_i x_j[i] gy_j[i + m],  gy_j[n] = g[frame j + n - start],
 //   dL/dM_{j,k} = (c_k / S0) sum_m win[m] cos(2 pi k (m - shift) / S0) dL/dh_j[m].
 #pragma once
-#include "harmonic_fast.cuh"
+#include "harmonic_common.cuh"
 #include "noise_fused.cuh"
 
 namespace ddsp {
 
 // ---------------------------------------------------------------------------
-// Harmonic backward.  Same tiling as harmonic_fast_kernel (grid (tiles, B), 256
+// Harmonic backward.  Same tiling as the first fused forward kernel (grid (tiles, B), 256
 // threads, one warp per frame pass, lane = samples r and r + 32).
 // ---------------------------------------------------------------------------
 constexpr int kHbThreads = 256;

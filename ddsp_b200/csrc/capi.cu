@@ -9,12 +9,11 @@
 #include "common.cuh"
 #include "controls.cuh"
 #include "harmonic.cuh"
-#include "harmonic_fast.cuh"
-#include "harmonic_v2.cuh"
+#include "harmonic_common.cuh"
 #include "harmonic_v3.cuh"
 #include "noise.cuh"
 #include "noise_fused.cuh"
-#include "noise_pipe.cuh"
+#include "noise_ring.cuh"
 #include "host_pipeline.cuh"
 #include "backward.cuh"
 #include "harmonic_bwd2.cuh"
@@ -65,17 +64,7 @@ static int set_smem(K kernel, size_t bytes, const char* name) {
 using namespace ddsp;
 
 namespace ddsp {
-// v3 is the product kernel; DDSP_B200_HARM_IMPL=v2 / fast select the earlier
-// generations for A/B measurements (tools/harm_sweep.py).
 static inline int launch_harmonic_best(const HarmonicParams& p, cudaStream_t st) {
-  static const int impl = [] {
-    const char* e = getenv("DDSP_B200_HARM_IMPL");
-    if (e != nullptr && strcmp(e, "fast") == 0) return 1;
-    if (e != nullptr && strcmp(e, "v2") == 0) return 2;
-    return 3;
-  }();
-  if (impl == 1) return launch_harmonic_fast(p, st);
-  if (impl == 2) return launch_harmonic_v2(p, st);
   return launch_harmonic_v3(p, st);
 }
 }  // namespace ddsp
@@ -154,7 +143,7 @@ int ddsp_b200_harmonic_forward(const float* f0_hz, const float* amps,
   p.init_phase = nullptr; p.final_phase = nullptr; p.mask_nyquist = 1;
   cudaStream_t st = (cudaStream_t)stream;
 
-  if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_fast_supported(p)) {
+  if (phase_mode == DDSP_B200_PHASE_RECURRENCE && harmonic_fused_supported(p)) {
     int rc = launch_harmonic_best(p, st);
     if (rc != 1) return rc;   // 1 = declined, fall through to the generic path
   }
@@ -422,7 +411,7 @@ static int decoder_forward_impl(const float* amps_raw, const float* hd_raw,
   p.init_phase = nullptr; p.final_phase = nullptr; p.mask_nyquist = 1;
   // The single-pass pipeline exists for the decoder regime only; everything
   // else goes through get_controls + the two *_forward calls.
-  DDSP_REQUIRE(N % F == 0 && B <= 65535 && harmonic_fast_supported(p) &&
+  DDSP_REQUIRE(N % F == 0 && B <= 65535 && harmonic_fused_supported(p) &&
                    noise_fused_supported(F, nb, N, window_size),
                DDSP_B200_E_UNSUPPORTED,
                "decoder_forward: shape outside the fused decoder path "

@@ -45,7 +45,7 @@ struct Chain {
 
 __device__ __forceinline__ void chain_seed(Chain& c, uint32_t p,
                                            const float2* __restrict__ tab) {
-  hv2::Osc o;
+  hcm::Osc o;
   hv3::osc_seed(o, p, tab);
   c.S = o.v;
   c.sigma = o.sigma;
@@ -84,7 +84,7 @@ harmonic_backward2_kernel(HarmonicParams p, const float* __restrict__ grad,
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) sRedD[warp] = part;
   }
-  for (int j = tid; j < kSinTab; j += NT) sTab[j] = hv2::g_sincos256[j];
+  for (int j = tid; j < kSinTab; j += NT) sTab[j] = hcm::g_sincos256[j];
   const float inv_hop = 1.0f / (float)hop;
   const int w0f = warp * FW;
   const int nfw = max(0, min(FW, nfr - w0f));
@@ -156,8 +156,8 @@ harmonic_backward2_kernel(HarmonicParams p, const float* __restrict__ grad,
     const float4 fa = *reinterpret_cast<const float4*>(&rec->f_lo);
     const unsigned long long D = ((unsigned long long)Dk.y << 32) | Dk.x;
     const int kc_a = (int)Dk.z, kc_b = (int)Dk.w;
-    const uint32_t pa = hv2::phase32(PA.x, PA.y, D, c1a, c2a);
-    const uint32_t pb = hv2::phase32(PA.x, PA.y, D, c1b, c2b);
+    const uint32_t pa = hcm::phase32(PA.x, PA.y, D, c1a, c2a);
+    const uint32_t pb = hcm::phase32(PA.x, PA.y, D, c1b, c2b);
     const float ga = gb[(size_t)li * hop + ra], gv = gb[(size_t)li * hop + rb];
     const float u1a = ga * w1a, u0a = ga - u1a, u1b = gv * w1b, u0b = gv - u1b;
     float* g0row = G0 + ((size_t)b * F + i0 + w0f + li) * K;

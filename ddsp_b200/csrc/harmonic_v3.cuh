@@ -1,6 +1,7 @@
 // harmonic_v3: third generation of the fused harmonic kernel (hop % 64 == 0).
-// Maths and every bit-level decision are those of harmonic_fast.cuh /
-// harmonic_v2.cuh (closed-form 64-bit fixed-point phase, Reinsch chains over the
+// Maths and every bit-level decision are those of the first two generations
+// (profiles/experiments/harmonic_fast.cuh.txt, harmonic_v2.cuh.txt; shared pieces in
+// harmonic_common.cuh: closed-form 64-bit fixed-point phase, Reinsch chains over the
 // harmonics in (odd, even) f32x2 lanes, per-row accumulators, live-count Nyquist
 // culling, get_controls fused into the slab staging).  What changed is the
 // instruction budget OUTSIDE the oscillator loop - ncu on v2 at B = 256
@@ -20,7 +21,7 @@
 //     re-summing f0[0 .. g0) from global memory in double precision;
 //   * per-lane constants and the Hann weights come out of the frame loop.
 #pragma once
-#include "harmonic_v2.cuh"
+#include "harmonic_common.cuh"
 
 namespace ddsp {
 namespace hv3 {
@@ -59,20 +60,20 @@ __host__ __device__ inline Smem smem_layout(int FW, int Kp, int hop) {
   return s;
 }
 
-using hv2::Osc;
-using hv2::osc_group;
-using hv2::osc_finish;
-using hv2::phase32;
-using hv2::mask4;
+using hcm::Osc;
+using hcm::osc_group;
+using hcm::osc_finish;
+using hcm::phase32;
+using hcm::mask4;
 
 // Harmonic.get_controls for up to four rows (r0 .. r0+3 of this warp's block) in
 // shared memory, 8 lanes per row: exp_sigmoid on the live prefix, zeros above it,
 // row normalisation with safe_divide (synths.py:110-117, core.py:894-907).  Same
-// arithmetic as hv2::controls_rows; the values stay in registers between the sum
+// arithmetic as hcm::controls_rows; the values stay in registers between the sum
 // and the normalisation (one store instead of store / load / store), only as many
 // 8-group passes run as the longest of the four rows needs (usually one), and the
 // zero fill of the masked tail is a separate tight loop.  Rows of up to 128
-// harmonics; wider rows take hv2::controls_rows.
+// harmonics; wider rows take hcm::controls_rows.
 __device__ __forceinline__ void controls_rows4(float* __restrict__ sXw,
                                                const int* __restrict__ sLive, int r0,
                                                int nrows, int Kp, bool raw_scale,
@@ -319,7 +320,7 @@ harmonic_v3_kernel(HarmonicParams p, int use_tma, int FW) {
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) sRedD[warp] = part;
   }
-  for (int j = tid; j < kSinTab; j += NT) sTab[j] = hv2::g_sincos256[j];
+  for (int j = tid; j < kSinTab; j += NT) sTab[j] = hcm::g_sincos256[j];
   const float inv_hop = 1.0f / (float)hop;
   if (HOPT != 64) {
     for (int r = tid; r < hop; r += NT) {
@@ -424,7 +425,7 @@ harmonic_v3_kernel(HarmonicParams p, int use_tma, int FW) {
           controls_rows4(sXw, sLive, r0, nrows, Kp, raw_scale, lane);
       } else {
         for (int r0 = 0; r0 < nrows; r0 += 4)
-          hv2::controls_rows(sXw, sLive, r0, nrows, Kp, raw_scale, lane);
+          hcm::controls_rows(sXw, sLive, r0, nrows, Kp, raw_scale, lane);
       }
     }
     if (last && rows_in < nfr + 1) {                    // frame F := frame F-1

@@ -1,8 +1,9 @@
 // noise_ring: FilteredNoise.get_signal for the decoder shape (n_frequencies = 65,
 // frame = 64 samples, 128-tap IR; ae.gin:60-68), third generation.  Same maths as
-// noise_fused.cuh / noise_pipe.cuh (windowed zero-phase IR per frame by E/O cosine
+// noise_fused.cuh (windowed zero-phase IR per frame by E/O cosine
 // sums, Philox noise, time-varying FIR == the reference's framed FFT convolution
-// + overlap-add + crop, core.py:1382-1473); the second generation was bound by
+// + overlap-add + crop, core.py:1382-1473); the second generation
+// (profiles/experiments/noise_pipe.cuh.txt) was bound by
 // shared-memory bandwidth (67 % of LSU wavefronts at 47 % FMA-pipe utilisation,
 // profiles/r01_ncu_summary_v7.txt) and by consumer warps marching in lock step
 // through an overlap-add buffer.  What changed:
@@ -622,6 +623,20 @@ inline int launch_noise_ring(const float* mags, const float* noise, uint64_t see
   }
   DDSP_CHECK_LAUNCH("filtered_noise_forward(ring)");
   return 0;
+}
+
+// noise_ring for the decoder shape (65 bands, 64-sample frames, 128 taps), the
+// generic fused kernel (noise_fused.cuh) for every other shape it supports.
+inline int launch_noise_best(const float* mags, const float* noise, uint64_t seed,
+                             uint64_t offset, float* audio, int B, int F, int nb,
+                             int N, int window_size, int accumulate,
+                             cudaStream_t st, int raw = 0, float bias = 0.f,
+                             int item_base = 0, int overlap_previous = 0) {
+  if (noise_ring_supported(F, nb, N, window_size))
+    return launch_noise_ring(mags, noise, seed, offset, audio, B, F, N, accumulate,
+                             st, raw, bias, item_base, overlap_previous);
+  return launch_noise_fused(mags, noise, seed, offset, audio, B, F, nb, N,
+                            window_size, accumulate, st, raw, bias, item_base);
 }
 
 }  // namespace ddsp

@@ -380,3 +380,47 @@ def test_decoder_is_deterministic_at_full_size():
   torch.cuda.synchronize()
   assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
   assert torch.isfinite(outs[0]).all()
+
+
+def test_noise_ring_stress_random_shapes_against_the_generic_path():
+  """compute-sanitizer's racecheck does not model the mbarrier hand-offs of the
+  warp-specialised noise kernel (it flags every producer -> consumer edge), so the
+  race question is put empirically: ~900 launches over random batch / frame counts
+  (every segment geometry: items shorter than a tile, CTA ranges cut mid-item, ring
+  wrap-around), back to back on one stream, each result compared (a) bit for bit
+  with a repeat of the same launch and (b) with the generic, unspecialised path -
+  separate impulse-response and FIR kernels, no ring, no warp roles - to 2e-6 of
+  the peak.  A stale tap row or a half-written noise row would be an O(1) error."""
+  from ddsp_b200 import _lib
+  lib = _lib.load()
+  rng = np.random.default_rng(20240)
+  st = torch.cuda.current_stream().cuda_stream
+  worst = 0.0
+  for trial in range(300):
+    B = int(rng.integers(1, 9))
+    F = int(rng.choice([3, 5, 17, 31, 32, 33, 63, 64, 65, 97, 128, 250, 333])) \
+        if trial % 3 else int(rng.integers(3, 400))
+    N = F * 64
+    mags = torch.rand((B, F, 65), device='cuda') * 1.5
+    noise = torch.rand((B, N), device='cuda') * 2 - 1
+    base = torch.randn((B, N), device='cuda') if trial % 2 else None
+    outs = []
+    for rep in range(3):
+      out = base.clone() if base is not None else torch.empty((B, N), device='cuda')
+      _lib.check(lib.ddsp_b200_filtered_noise_forward(
+          mags.data_ptr(), noise.data_ptr(), 0, 0, out.data_ptr(), B, F, 65, N, 0,
+          int(base is not None), None, 0, st))
+      outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (trial, B, F)
+    # generic path: IRs to HBM, then the plain time-varying FIR kernel
+    ir = core.frequency_impulse_response(mags, 0)
+    want = torch.empty((B, N), device='cuda') if base is None else base.clone()
+    _lib.check(lib.ddsp_b200_fir_time_varying(
+        noise.data_ptr(), ir.data_ptr(), want.data_ptr(), B, N, F, 128, B, _lib.PAD_SAME,
+        -1, int(base is not None), st))
+    ref = want - base if base is not None else want
+    got = outs[0] - base if base is not None else outs[0]
+    err = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-20))
+    worst = max(worst, err)
+    assert err < 2e-5, (trial, B, F, err)
+  assert worst < 2e-5
