@@ -201,6 +201,105 @@ lc_mac_ifft(const float2* __restrict__ Z, const float2* __restrict__ H,
   }
 }
 
+// ---- frequency-sliced multiply-accumulate ---------------------------------------
+// For a fixed frequency bin the partition sum out[j] = sum_p Z[j - p] H[p] is a 1-D
+// convolution along the BLOCK index, and bins do not interact.  One CTA therefore
+// takes a slice of CH bins of one item, stages ALL its input windows and ALL the
+// partitions of the impulse response for that slice in shared memory (33 + 47
+// spectra slices = 82 KB at the Reverb shape, CH = 128) and produces every output
+// block of the slice from there: each spectrum element is read from L2 exactly
+// once (the per-block kernel above re-reads 2 P / JT spectra per output block:
+// 4.7 GB of L2 traffic at B = 256 against 0.6 GB here).  A thread owns one bin
+// and four consecutive output blocks at a time, the windows sliding through
+// registers.  Spectra of the output blocks go to Wf [B, n_blocks, M]; lc_ifft turns
+// them into w.
+struct MacGeom {
+  int CH, n_slices;
+  size_t smem;
+};
+__host__ inline MacGeom mac_geom(int n_in, int P, size_t max_smem) {
+  MacGeom g;
+  g.CH = 128;
+  while (g.CH > 8 && sizeof(float2) * (size_t)(n_in + P) * g.CH > max_smem) g.CH >>= 1;
+  g.n_slices = M / g.CH;
+  g.smem = sizeof(float2) * (size_t)(n_in + P) * g.CH;
+  return g;
+}
+
+__global__ void __launch_bounds__(THREADS)
+lc_mac_sliced(const float2* __restrict__ Z, const float2* __restrict__ H,
+              float2* __restrict__ Wf, int n_in, int P, int ir_batch_stride, int j_first,
+              int n_blocks, int CH) {
+  extern __shared__ __align__(16) unsigned char lc_smem[];
+  float2* sZ = reinterpret_cast<float2*>(lc_smem);          // [n_in][CH]
+  float2* sH = sZ + (size_t)n_in * CH;                      // [P][CH]
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const int f0 = blockIdx.x * CH;
+  const float2* Zb = Z + (size_t)b * n_in * M + f0;
+  const float2* Hb = H + (size_t)b * ir_batch_stride + f0;
+  for (int i = tid; i < n_in * CH; i += THREADS) {
+    const int w = i / CH, f = i - w * CH;
+    sZ[i] = Zb[(size_t)w * M + f];
+  }
+  for (int i = tid; i < P * CH; i += THREADS) {
+    const int q = i / CH, f = i - q * CH;
+    sH[i] = Hb[(size_t)q * M + f];
+  }
+  __syncthreads();
+  const int f = tid % CH, jg = tid / CH, n_jg = THREADS / CH;
+  float2* out = Wf + (size_t)b * n_blocks * M + f0 + f;
+  for (int t = jg; t * 4 < n_blocks; t += n_jg) {           // tiles of four blocks
+    const int j0 = j_first + 4 * t;
+    float2 acc[4], zw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+    const int p_lo = max(0, j0 - (n_in - 1)), p_hi = min(P - 1, j0 + 3);
+    auto window = [&](int w) {
+      return (w >= 0 && w < n_in) ? sZ[(size_t)w * CH + f] : make_float2(0.f, 0.f);
+    };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) zw[k] = window(j0 + k - p_lo);
+    for (int pb = p_lo; pb <= p_hi; pb += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = pb + u;
+        if (p <= p_hi) {
+          const float2 h = sH[(size_t)p * CH + f];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 z = zw[(k - u) & 3];
+            acc[k].x = fmaf(z.x, h.x, fmaf(-z.y, h.y, acc[k].x));
+            acc[k].y = fmaf(z.x, h.y, fmaf(z.y, h.x, acc[k].y));
+          }
+          zw[(3 - u) & 3] = window(j0 - (p + 1));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (4 * t + k < n_blocks) out[(size_t)(4 * t + k) * M] = acc[k];
+  }
+}
+
+// w block j_first + blockIdx.x of item b: inverse transform of its spectrum.
+__global__ void __launch_bounds__(THREADS)
+lc_ifft(const float2* __restrict__ Wf, float2* __restrict__ W, int n_out, int j_first,
+        int n_blocks) {
+  __shared__ float2 s[M];
+  __shared__ float2 tw[M / 2];
+  const int tid = threadIdx.x, jj = blockIdx.x, b = blockIdx.y;
+  fill_twiddles(tw, tid);
+  const float2* src = Wf + ((size_t)b * n_blocks + jj) * M;
+  for (int i = tid; i < M; i += THREADS) s[i] = src[i];
+  ifft_dit(s, tw, tid);
+  const float scale = 1.0f / (float)M;
+  float2* out = W + ((size_t)b * n_out + (j_first + jj)) * L;
+  for (int i = tid; i < L; i += THREADS) {
+    const float2 v = s[L + i];
+    out[i] = make_float2(v.x * scale, v.y * scale);
+  }
+}
+
 // y[b, n] = Re w[n + start] + Im w[n + start - N2], n < out_len (crop of
 // crop_and_compensate_delay, core.py:1338-1379).  w is valid on [0, n_out * L).
 __global__ void __launch_bounds__(256)
