@@ -840,8 +840,8 @@ size_t ddsp_b200_fft_convolve_lti_workspace(int B, int N, int S, int ir_batch) {
   if (B <= 0 || N <= 0 || S <= 0 || (ir_batch != 1 && ir_batch != B)) return 0;
   const lc::Geom g = lc::geom(N, S);
   const size_t z = (size_t)B * g.n_in * lc::M, h = (size_t)ir_batch * g.P * lc::M,
-               w = (size_t)B * g.w_len, wf = (size_t)B * g.n_out * lc::M;
-  return sizeof(float2) * (z + h + w + wf) + 256;
+               w = (size_t)B * g.w_len;
+  return sizeof(float2) * (z + h + w) + 256;
 }
 
 int ddsp_b200_fft_convolve_lti(const float* audio, const float* impulse_response,
@@ -872,7 +872,6 @@ int ddsp_b200_fft_convolve_lti(const float* audio, const float* impulse_response
   float2* Z = reinterpret_cast<float2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   float2* H = Z + (size_t)B * g.n_in * lc::M;
   float2* W = H + (size_t)ir_batch * g.P * lc::M;
-  float2* Wf = W + (size_t)B * g.w_len;
   cudaStream_t st = (cudaStream_t)stream;
   DDSP_REQUIRE((flags & ~3) == 0, DDSP_B200_E_INVALID,
                "fft_convolve_lti: bad flags %d", flags);
@@ -889,25 +888,14 @@ int ddsp_b200_fft_convolve_lti(const float* audio, const float* impulse_response
   const int j_first = lo_pos / lc::L;
   const int j_last = std::min(g.n_out - 1, (hi_pos - 1) / lc::L);
   const int n_blocks = j_last - j_first + 1;
-  const lc::MacGeom mg = lc::mac_geom(g.n_in, g.P, kMaxDynSmem);
-  if (mg.smem <= kMaxDynSmem) {
-    // frequency-sliced: every spectrum element is read once
-    int rc = set_smem(lc::lc_mac_sliced, mg.smem, "fft_convolve_lti");
-    if (rc) return rc;
-    lc::lc_mac_sliced<<<dim3(mg.n_slices, B), lc::THREADS, mg.smem, st>>>(
-        Z, H, Wf, g.n_in, g.P, ir_batch == 1 ? 0 : g.P * lc::M, j_first, n_blocks, mg.CH);
-    DDSP_CHECK_LAUNCH("fft_convolve_lti(multiply-accumulate)");
-    lc::lc_ifft<<<dim3(n_blocks, B), lc::THREADS, 0, st>>>(Wf, W, g.n_out, j_first, n_blocks);
-    DDSP_CHECK_LAUNCH("fft_convolve_lti(inverse)");
-  } else {
-    // very long signals: the slices do not fit shared memory; block-tiled variant
+  {
     int rc = set_smem(lc::lc_mac_ifft, lc::kMacSmem, "fft_convolve_lti");
     if (rc) return rc;
-    lc::lc_mac_ifft<<<dim3((n_blocks + lc::JT - 1) / lc::JT, B), lc::THREADS,
-                      lc::kMacSmem, st>>>(
-        Z, H, W, g.n_in, g.P, g.n_out, ir_batch == 1 ? 0 : g.P * lc::M, j_first, n_blocks);
-    DDSP_CHECK_LAUNCH("fft_convolve_lti(multiply-accumulate + inverse)");
   }
+  lc::lc_mac_ifft<<<dim3((n_blocks + lc::JT - 1) / lc::JT, B), lc::THREADS, lc::kMacSmem,
+                    st>>>(
+      Z, H, W, g.n_in, g.P, g.n_out, ir_batch == 1 ? 0 : g.P * lc::M, j_first, n_blocks);
+  DDSP_CHECK_LAUNCH("fft_convolve_lti(multiply-accumulate + inverse)");
   const int cgrid = std::min((out_len + 255) / 256, 8 * kNumSMs);
   lc::lc_combine<<<dim3(cgrid, B), 256, 0, st>>>(W, out, g.n2, g.w_len, start, out_len,
                                                N + S - 1, accumulate, j_first * lc::L,

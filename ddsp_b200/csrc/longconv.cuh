@@ -8,10 +8,10 @@
 //   * REAL -> COMPLEX PACKING WITHOUT WASTE.  Convolution with a real h is linear
 //     over complex inputs, so the two time-halves of an item ride in one complex
 //     signal: z[n] = x[n] + i x[n + N2], w = z * h, y[n] = Re w[n] + Im w[n - N2].
-//   * NO BIT REVERSAL.  The forward transform is decimation-in-frequency (natural
-//     in, bit-reversed out), the inverse decimation-in-time (bit-reversed in,
+//   * NO REORDERING PASS.  The forward transform is decimation-in-frequency (natural
+//     in, digit-reversed out), the inverse decimation-in-time (digit-reversed in,
 //     natural out); the spectra only ever meet in element-wise products, so both
-//     sides simply live in bit-reversed order.
+//     sides simply live in digit-reversed order.  Radix 4 (2048 = 4^5 * 2).
 //   * Overlap-save: input window j = samples [(j-1) L, (j+1) L) of z; IR partition
 //     p = h[p L, (p+1) L) zero-padded to 2 L; output block j = last L samples of
 //     IFFT(sum_p Z_{j-p} H_p).
@@ -39,42 +39,74 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
 
-// tw[m] = exp(-2 pi i m / M), m < M / 2
+constexpr int TWN = 3 * M / 4;      // twiddles tw[m] = exp(-2 pi i m / M), m < 3 M / 4
+
 __device__ __forceinline__ void fill_twiddles(float2* tw, int tid) {
-  for (int m = tid; m < M / 2; m += THREADS) {
+  for (int m = tid; m < TWN; m += THREADS) {
     float s, c;
     sincospif(-2.0f * (float)m / (float)M, &s, &c);
     tw[m] = make_float2(c, s);
   }
 }
 
-// forward, decimation in frequency: natural order in, bit-reversed order out
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+__device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }   // a * (+i)
+
+// Forward transform, decimation in frequency, 2048 = 4^5 * 2: five radix-4 stages
+// (quarter spans 512, 128, 32, 8, 2) and one radix-2 stage; natural order in,
+// digit-reversed order out.  A stage is y = T F4 x per group (F4 the 4-point DFT, T
+// the twiddles W^(k m)); six barriers instead of the eleven of a radix-2 network.
 __device__ __forceinline__ void fft_dif(float2* s, const float2* tw, int tid) {
 #pragma unroll 1
-  for (int half = M / 2, sh = 0; half >= 1; half >>= 1, ++sh) {
+  for (int q = M / 4, sh = 0; q >= 2; q >>= 2, sh += 2) {      // W = tw[1 << sh]
     __syncthreads();
-    for (int i = tid; i < M / 2; i += THREADS) {
-      const int k = i & (half - 1);
-      const int a = ((i - k) << 1) + k, b = a + half;
-      const float2 u = s[a], v = s[b];
-      s[a] = make_float2(u.x + v.x, u.y + v.y);
-      s[b] = cmul(make_float2(u.x - v.x, u.y - v.y), tw[k << sh]);
+    for (int i = tid; i < M / 4; i += THREADS) {
+      const int k = i & (q - 1);
+      const int base = ((i - k) << 2) + k;
+      const float2 x0 = s[base], x1 = s[base + q], x2 = s[base + 2 * q], x3 = s[base + 3 * q];
+      const float2 a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = csub(x1, x3);
+      const int t = k << sh;
+      s[base] = cadd(a, c);
+      s[base + q] = cmul(cadd(b, mul_mi(d)), tw[t]);
+      s[base + 2 * q] = cmul(csub(a, c), tw[2 * t]);
+      s[base + 3 * q] = cmul(cadd(b, mul_pi(d)), tw[3 * t]);
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < M / 2; i += THREADS) {                 // radix-2, span 1
+    const float2 u = s[2 * i], v = s[2 * i + 1];
+    s[2 * i] = cadd(u, v);
+    s[2 * i + 1] = csub(u, v);
   }
   __syncthreads();
 }
 
-// inverse (unscaled), decimation in time: bit-reversed order in, natural order out
+// Inverse (unscaled): the stages of fft_dif undone in reverse order, each as
+// x = F4^H conj(T) y; digit-reversed order in, natural order out.
 __device__ __forceinline__ void ifft_dit(float2* s, const float2* tw, int tid) {
+  __syncthreads();
+  for (int i = tid; i < M / 2; i += THREADS) {
+    const float2 u = s[2 * i], v = s[2 * i + 1];
+    s[2 * i] = cadd(u, v);
+    s[2 * i + 1] = csub(u, v);
+  }
 #pragma unroll 1
-  for (int half = 1, sh = LOGM - 1; half <= M / 2; half <<= 1, --sh) {
+  for (int q = 2, sh = 8; q <= M / 4; q <<= 2, sh -= 2) {
     __syncthreads();
-    for (int i = tid; i < M / 2; i += THREADS) {
-      const int k = i & (half - 1);
-      const int a = ((i - k) << 1) + k, b = a + half;
-      const float2 u = s[a], v = cmul_conj(s[b], tw[k << sh]);
-      s[a] = make_float2(u.x + v.x, u.y + v.y);
-      s[b] = make_float2(u.x - v.x, u.y - v.y);
+    for (int i = tid; i < M / 4; i += THREADS) {
+      const int k = i & (q - 1);
+      const int base = ((i - k) << 2) + k;
+      const int t = k << sh;
+      const float2 x0 = s[base], x1 = cmul_conj(s[base + q], tw[t]),
+                   x2 = cmul_conj(s[base + 2 * q], tw[2 * t]),
+                   x3 = cmul_conj(s[base + 3 * q], tw[3 * t]);
+      const float2 a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = csub(x1, x3);
+      s[base] = cadd(a, c);
+      s[base + q] = cadd(b, mul_pi(d));
+      s[base + 2 * q] = csub(a, c);
+      s[base + 3 * q] = cadd(b, mul_mi(d));
     }
   }
   __syncthreads();
@@ -88,7 +120,7 @@ __global__ void __launch_bounds__(THREADS)
 lc_fft_blocks(const float* __restrict__ src, float2* __restrict__ spec, int len,
               int n2, int n_blocks, int mode, int reverse) {
   __shared__ float2 s[M];
-  __shared__ float2 tw[M / 2];
+  __shared__ float2 tw[TWN];
   const int tid = threadIdx.x, j = blockIdx.x, b = blockIdx.y;
   const float* x = src + (size_t)b * len;
   fill_twiddles(tw, tid);
@@ -121,7 +153,7 @@ lc_fft_blocks(const float* __restrict__ src, float2* __restrict__ spec, int len,
 constexpr int JT = 4;
 constexpr int EPT = 4;                  // spectrum elements per thread per pass
 constexpr int PASSES = M / (THREADS * EPT);
-constexpr size_t kMacSmem = sizeof(float2) * ((size_t)JT * M + M / 2);
+constexpr size_t kMacSmem = sizeof(float2) * ((size_t)JT * M + TWN);
 
 __global__ void __launch_bounds__(THREADS, 2)
 lc_mac_ifft(const float2* __restrict__ Z, const float2* __restrict__ H,
@@ -129,7 +161,7 @@ lc_mac_ifft(const float2* __restrict__ Z, const float2* __restrict__ H,
             int j_first, int n_blocks) {
   extern __shared__ __align__(16) unsigned char lc_smem[];
   float2* sAcc = reinterpret_cast<float2*>(lc_smem);            // [JT][M]
-  float2* tw = sAcc + (size_t)JT * M;                           // [M / 2]
+  float2* tw = sAcc + (size_t)JT * M;                           // [TWN]
   const int tid = threadIdx.x, b = blockIdx.y;
   const int j0 = j_first + blockIdx.x * JT;
   const int jt_n = min(JT, j_first + n_blocks - j0);
@@ -198,105 +230,6 @@ lc_mac_ifft(const float2* __restrict__ Z, const float2* __restrict__ H,
       const float2 v = s[L + i];
       out[i] = make_float2(v.x * scale, v.y * scale);
     }
-  }
-}
-
-// ---- frequency-sliced multiply-accumulate ---------------------------------------
-// For a fixed frequency bin the partition sum out[j] = sum_p Z[j - p] H[p] is a 1-D
-// convolution along the BLOCK index, and bins do not interact.  One CTA therefore
-// takes a slice of CH bins of one item, stages ALL its input windows and ALL the
-// partitions of the impulse response for that slice in shared memory (33 + 47
-// spectra slices = 82 KB at the Reverb shape, CH = 128) and produces every output
-// block of the slice from there: each spectrum element is read from L2 exactly
-// once (the per-block kernel above re-reads 2 P / JT spectra per output block:
-// 4.7 GB of L2 traffic at B = 256 against 0.6 GB here).  A thread owns one bin
-// and four consecutive output blocks at a time, the windows sliding through
-// registers.  Spectra of the output blocks go to Wf [B, n_blocks, M]; lc_ifft turns
-// them into w.
-struct MacGeom {
-  int CH, n_slices;
-  size_t smem;
-};
-__host__ inline MacGeom mac_geom(int n_in, int P, size_t max_smem) {
-  MacGeom g;
-  g.CH = 128;
-  while (g.CH > 8 && sizeof(float2) * (size_t)(n_in + P) * g.CH > max_smem) g.CH >>= 1;
-  g.n_slices = M / g.CH;
-  g.smem = sizeof(float2) * (size_t)(n_in + P) * g.CH;
-  return g;
-}
-
-__global__ void __launch_bounds__(THREADS)
-lc_mac_sliced(const float2* __restrict__ Z, const float2* __restrict__ H,
-              float2* __restrict__ Wf, int n_in, int P, int ir_batch_stride, int j_first,
-              int n_blocks, int CH) {
-  extern __shared__ __align__(16) unsigned char lc_smem[];
-  float2* sZ = reinterpret_cast<float2*>(lc_smem);          // [n_in][CH]
-  float2* sH = sZ + (size_t)n_in * CH;                      // [P][CH]
-  const int tid = threadIdx.x, b = blockIdx.y;
-  const int f0 = blockIdx.x * CH;
-  const float2* Zb = Z + (size_t)b * n_in * M + f0;
-  const float2* Hb = H + (size_t)b * ir_batch_stride + f0;
-  for (int i = tid; i < n_in * CH; i += THREADS) {
-    const int w = i / CH, f = i - w * CH;
-    sZ[i] = Zb[(size_t)w * M + f];
-  }
-  for (int i = tid; i < P * CH; i += THREADS) {
-    const int q = i / CH, f = i - q * CH;
-    sH[i] = Hb[(size_t)q * M + f];
-  }
-  __syncthreads();
-  const int f = tid % CH, jg = tid / CH, n_jg = THREADS / CH;
-  float2* out = Wf + (size_t)b * n_blocks * M + f0 + f;
-  for (int t = jg; t * 4 < n_blocks; t += n_jg) {           // tiles of four blocks
-    const int j0 = j_first + 4 * t;
-    float2 acc[4], zw[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
-    const int p_lo = max(0, j0 - (n_in - 1)), p_hi = min(P - 1, j0 + 3);
-    auto window = [&](int w) {
-      return (w >= 0 && w < n_in) ? sZ[(size_t)w * CH + f] : make_float2(0.f, 0.f);
-    };
-#pragma unroll
-    for (int k = 0; k < 4; ++k) zw[k] = window(j0 + k - p_lo);
-    for (int pb = p_lo; pb <= p_hi; pb += 4) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int p = pb + u;
-        if (p <= p_hi) {
-          const float2 h = sH[(size_t)p * CH + f];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 z = zw[(k - u) & 3];
-            acc[k].x = fmaf(z.x, h.x, fmaf(-z.y, h.y, acc[k].x));
-            acc[k].y = fmaf(z.x, h.y, fmaf(z.y, h.x, acc[k].y));
-          }
-          zw[(3 - u) & 3] = window(j0 - (p + 1));
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (4 * t + k < n_blocks) out[(size_t)(4 * t + k) * M] = acc[k];
-  }
-}
-
-// w block j_first + blockIdx.x of item b: inverse transform of its spectrum.
-__global__ void __launch_bounds__(THREADS)
-lc_ifft(const float2* __restrict__ Wf, float2* __restrict__ W, int n_out, int j_first,
-        int n_blocks) {
-  __shared__ float2 s[M];
-  __shared__ float2 tw[M / 2];
-  const int tid = threadIdx.x, jj = blockIdx.x, b = blockIdx.y;
-  fill_twiddles(tw, tid);
-  const float2* src = Wf + ((size_t)b * n_blocks + jj) * M;
-  for (int i = tid; i < M; i += THREADS) s[i] = src[i];
-  ifft_dit(s, tw, tid);
-  const float scale = 1.0f / (float)M;
-  float2* out = W + ((size_t)b * n_out + (j_first + jj)) * L;
-  for (int i = tid; i < L; i += THREADS) {
-    const float2 v = s[L + i];
-    out[i] = make_float2(v.x * scale, v.y * scale);
   }
 }
 
