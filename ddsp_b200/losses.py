@@ -18,7 +18,7 @@ def mean_difference(target, value, loss_type='L1', weights=None):
     return torch.mean(difference**2 * weights)
   elif loss_type == 'COSINE':
     cos = torch.nn.functional.cosine_similarity(target, value, dim=-1)
-    return torch.mean((1.0 - cos) * (1.0 if weights is None else weights))
+    return torch.mean((1.0 - cos) * weights)   # weights is 1.0 when none were given
   else:
     raise ValueError('Loss type ({}), must be '
                      '"L1", "L2", or "COSINE"'.format(loss_type))

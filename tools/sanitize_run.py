@@ -49,7 +49,31 @@ e = dec({k: host.pin(inp[k]) for k in ['amps', 'harmonic_distribution', 'f0_hz',
 dec.close()
 f = ddsp_b200.Sinusoidal(n_samples=640)(torch.randn(2, 10, 6), torch.randn(2, 10, 6))
 g = ddsp_b200.Reverb()(torch.randn(2, 3000).cuda(), 0.01 * torch.randn(2, 2500).cuda())
+# round-2 kernels: harmonic_shifts / fused sinusoidal bank, cubic + 4-D resample,
+# angular_cumsum (exact and TF order), tf_sequential bank, long-IR convolution forward
+# and backward, d f0, f0 < 1 Hz frames
+shifts = 0.01 * torch.randn(B, F, K, device='cuda')
+h2 = core.harmonic_synthesis(feats['f0_hz'], outs['harmonic']['controls']['amplitudes'],
+                             harmonic_shifts=shifts,
+                             harmonic_distribution=outs['harmonic']['controls']['harmonic_distribution'],
+                             n_samples=N)
+r4 = core.resample(torch.randn(2, 9, 3, 2), 37, method='cubic', add_endpoint=False)
+om = 0.3 * torch.rand(2, 2300, 3, device='cuda')
+pc = core.angular_cumsum(om); ps = core.angular_cumsum(om, tf_sequential=True)
+ob = core.oscillator_bank(200 + 3000 * torch.rand(2, 700, 4, device='cuda'),
+                          torch.rand(2, 700, 4, device='cuda'), phase_mode='tf_sequential',
+                          use_angular_cumsum=True)
+xa = torch.randn(2, 5000, device='cuda', requires_grad=True)
+hi = (0.02 * torch.randn(1, 4500, device='cuda')).requires_grad_(True)
+core.fft_convolve(xa, hi, padding='same', delay_compensation=0).square().mean().backward()
+f0g = feats['f0_hz'].clone()
+f0g[:, 5:9] = 0.3
+f0g.requires_grad_(True)
+ag.decoder_train(feats['amps'], feats['harmonic_distribution'], f0g,
+                 feats['noise_magnitudes'], n_samples=N, window_size=0).abs().mean().backward()
 torch.cuda.synchronize()
+assert torch.isfinite(h2).all() and torch.isfinite(r4).all() and torch.isfinite(ob).all()
+assert torch.isfinite(xa.grad).all() and torch.isfinite(hi.grad).all() and torch.isfinite(f0g.grad).all()
 assert torch.isfinite(e).all() and torch.isfinite(f).all() and torch.isfinite(g).all()
 print('sanitize_run ok', float(a.abs().mean()), float(b.abs().mean()),
       float(c.abs().mean()), float(d.abs().mean()),
