@@ -58,9 +58,9 @@ def _measured_peaks():
 
 class ClockSampler:
   """Samples SM clocks / throttle reasons through NVML while the GPU is under
-  load.  A step of this workload is tens of microseconds, so a polling
-  `nvidia-smi -lms` process never lands a sample inside a short timed region;
-  an in-process NVML thread polls every ~1 ms instead.  Samples are stamped so
+  load.  The timed region of this workload is ~16 ms, so a polling
+  `nvidia-smi -lms` process rarely lands a sample inside it; an in-process NVML
+  thread polls every ~2 ms instead.  Samples are stamped so
   the timed window can be separated from the rest of the load window."""
   REASONS = {
       'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40,
@@ -99,7 +99,7 @@ class ClockSampler:
           except Exception as e:  # pylint: disable=broad-except
             self.err = repr(e)
             return
-          time.sleep(0.0005)
+          time.sleep(0.002)     # ~8 samples in a 16 ms timed region, no GIL pressure
 
       self.thread = threading.Thread(target=loop, daemon=True)
       self.thread.start()

@@ -215,8 +215,10 @@ struct NoiseBwdParams {
   int B, F, nb, N, frame, start, S, ylen;
   int xS, gS, hS, nh;               // smem strides; nh = S0/2 + 1
   int tiles_per_item, n_tiles;
+  int eo_tab;                       // 1: [nh][kEoStride] cosine table behind the rows (nb = 65)
   IrGeom g;
 };
+constexpr int kEoStride = 36;       // 33 columns k = 0..32, padded to float4s
 
 __global__ void __launch_bounds__(kNbThreads)
 noise_backward_kernel(NoiseBwdParams p) {
@@ -226,6 +228,7 @@ noise_backward_kernel(NoiseBwdParams p) {
   float* sX = sWin + p.S;                        // [32][xS]
   float* sG = sX + 32 * p.xS;                    // [32][gS]   gy rows
   float* sH = sG + 32 * p.gS;                    // [32][hS]   dh rows, then dh0
+  float* sEo = sH + 32 * p.hS;                   // [nh][kEoStride] cos(2 pi k n / S0), k <= 32
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = p.nb, S = p.S, S0 = p.g.S0, frame = p.frame;
   for (int i = tid; i < S0; i += kNbThreads) sCos[i] = cospif(2.0f * (float)i / (float)S0);
@@ -233,6 +236,12 @@ noise_backward_kernel(NoiseBwdParams p) {
     int idx; float w;
     ir_tap(p.g, j, &idx, &w);
     sWin[j] = w;
+  }
+  if (p.eo_tab) {
+    for (int e = tid; e < p.nh * kEoStride; e += kNbThreads) {
+      const int n = e / kEoStride, k = e - n * kEoStride;
+      sEo[e] = (k <= 32) ? cospif(2.0f * (float)((k * n) % p.g.S0) / (float)p.g.S0) : 0.f;
+    }
   }
   for (int e = tid; e < 32 * p.xS; e += kNbThreads) sX[e] = 0.f;   // pads stay zero
   for (int e = tid; e < 32 * p.gS; e += kNbThreads) sG[e] = 0.f;
@@ -305,7 +314,42 @@ noise_backward_kernel(NoiseBwdParams p) {
       }
     }
     __syncthreads();
-    {
+    if (p.eo_tab) {
+      // nb = 65 (S0 = 128): cos(2 pi (64 - k) n / 128) = (-1)^n cos(2 pi k n / 128), so
+      // with E[k] / O[k] the sums over even / odd n, dM_k = c (E + O) and dM_{64-k} =
+      // c (E - O): half the multiplies, four columns per broadcast LDS.128.  Warp w
+      // owns k = 4 w .. 4 w + 3; k = 32 rides with warp 0.
+      const float* d0 = sH + lane * p.hS + S;
+      const float invS0 = 1.0f / (float)S0;
+      const int k0 = 4 * warp;
+      float4 aE = make_float4(0.f, 0.f, 0.f, 0.f), aO = aE;
+      float e32 = 0.f;                                  // k = 32: odd n contribute 0
+      for (int n = 0; n < p.nh; n += 2) {
+        const float de = d0[n];
+        const float4 te = *reinterpret_cast<const float4*>(sEo + n * kEoStride + k0);
+        aE.x = fmaf(de, te.x, aE.x); aE.y = fmaf(de, te.y, aE.y);
+        aE.z = fmaf(de, te.z, aE.z); aE.w = fmaf(de, te.w, aE.w);
+        if (warp == 0) e32 = fmaf(de, sEo[n * kEoStride + 32], e32);
+        if (n + 1 < p.nh) {
+          const float dd = d0[n + 1];
+          const float4 to = *reinterpret_cast<const float4*>(sEo + (n + 1) * kEoStride + k0);
+          aO.x = fmaf(dd, to.x, aO.x); aO.y = fmaf(dd, to.y, aO.y);
+          aO.z = fmaf(dd, to.z, aO.z); aO.w = fmaf(dd, to.w, aO.w);
+        }
+      }
+      if (j0 + lane < p.F) {
+        float* dm = p.dmags + ((size_t)b * p.F + j0 + lane) * nb;
+        const float E[4] = {aE.x, aE.y, aE.z, aE.w}, O[4] = {aO.x, aO.y, aO.z, aO.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = k0 + c;                         // 0 .. 31
+          const float ck = (k == 0) ? invS0 : 2.0f * invS0;
+          dm[k] = ck * (E[c] + O[c]);
+          dm[64 - k] = ck * (E[c] - O[c]);              // k = 0 -> 64 (same end weight)
+        }
+        if (warp == 0) dm[32] = 2.0f * invS0 * e32;
+      }
+    } else {
       const float* d0 = sH + lane * p.hS + S;
       const float invS0 = 1.0f / (float)S0;
       for (int k = warp; k < nb; k += kNbThreads / 32) {

@@ -775,7 +775,9 @@ int ddsp_b200_filtered_noise_backward(const float* grad_audio, const float* nois
   DDSP_REQUIRE(n_tiles < (1ll << 31), DDSP_B200_E_INVALID,
                "filtered_noise_backward: too many tiles");
   p.n_tiles = (int)n_tiles;
-  const size_t smem = sizeof(float) * ((size_t)p.g.S0 + p.S + 32 * (size_t)(p.xS + p.gS + p.hS));
+  p.eo_tab = (nb == 65 && p.g.S0 == 128 && p.nh == 65) ? 1 : 0;
+  const size_t smem = sizeof(float) * ((size_t)p.g.S0 + p.S + 32 * (size_t)(p.xS + p.gS + p.hS) +
+                                       (p.eo_tab ? (size_t)p.nh * kEoStride : 0));
   DDSP_REQUIRE(smem <= kMaxDynSmem, DDSP_B200_E_UNSUPPORTED,
                "filtered_noise_backward: shape needs %zu B of shared memory", smem);
   int rc = set_smem(noise_backward_kernel, smem, "filtered_noise_backward");
