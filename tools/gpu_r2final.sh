@@ -19,4 +19,5 @@ ncu -i $O/${TAG}_full_b256.ncu-rep --page raw --csv > $O/${TAG}_raw.csv 2>/dev/n
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $O/${TAG}_memcheck.log 2>&1; tail -3 $O/${TAG}_memcheck.log
 timeout 900 compute-sanitizer --tool synccheck python tools/sanitize_run.py > $O/${TAG}_synccheck.log 2>&1; tail -3 $O/${TAG}_synccheck.log
 timeout 300 python tools/reverb_time.py > $O/${TAG}_reverb.log 2>&1; cat $O/${TAG}_reverb.log
+timeout 300 python tools/sinusoidal_time.py > $O/${TAG}_sinusoidal.log 2>&1; cat $O/${TAG}_sinusoidal.log
 tail -5 $O/${TAG}_pytest_gpu.log; cat $O/${TAG}_bench_n1.json; cat $O/${TAG}_bench_reference.json; cat $O/${TAG}_bench_c4.json
