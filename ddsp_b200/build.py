@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
   if not force and not is_stale():
     return LIB_PATH
   nvcc = os.environ.get('NVCC', 'nvcc')
-  cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [
+  extra = os.environ.get('DDSP_B200_NVCC_EXTRA', '').split()   # e.g. -DDDSP_HV3_MIN_CTAS=5
+  cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + [
       '-o', LIB_PATH] + _sources()
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:
