@@ -11,6 +11,7 @@
 #include "harmonic.cuh"
 #include "harmonic_common.cuh"
 #include "harmonic_v3.cuh"
+#include "harmonic_v4.cuh"
 #include "noise.cuh"
 #include "noise_fused.cuh"
 #include "noise_ring.cuh"
@@ -65,7 +66,15 @@ using namespace ddsp;
 
 namespace ddsp {
 static inline int launch_harmonic_best(const HarmonicParams& p, cudaStream_t st) {
-  return launch_harmonic_v3(p, st);
+  // A/B knob for measurements only (tools/README.md): DDSP_B200_HARM_IMPL=v3
+  static const bool use_v3 = [] {
+#ifdef DDSP_HARM_DEFAULT_V3
+    return true;
+#endif
+    const char* e = getenv("DDSP_B200_HARM_IMPL");
+    return e != nullptr && strcmp(e, "v3") == 0;
+  }();
+  return use_v3 ? launch_harmonic_v3(p, st) : launch_harmonic_v4(p, st);
 }
 }  // namespace ddsp
 
