@@ -10,7 +10,6 @@
 #include "controls.cuh"
 #include "harmonic.cuh"
 #include "harmonic_common.cuh"
-#include "harmonic_v3.cuh"
 #include "harmonic_v4.cuh"
 #include "noise.cuh"
 #include "noise_fused.cuh"
@@ -66,15 +65,7 @@ using namespace ddsp;
 
 namespace ddsp {
 static inline int launch_harmonic_best(const HarmonicParams& p, cudaStream_t st) {
-  // A/B knob for measurements only (tools/README.md): DDSP_B200_HARM_IMPL=v3
-  static const bool use_v3 = [] {
-#ifdef DDSP_HARM_DEFAULT_V3
-    return true;
-#endif
-    const char* e = getenv("DDSP_B200_HARM_IMPL");
-    return e != nullptr && strcmp(e, "v3") == 0;
-  }();
-  return use_v3 ? launch_harmonic_v3(p, st) : launch_harmonic_v4(p, st);
+  return launch_harmonic_v4(p, st);
 }
 }  // namespace ddsp
 

@@ -3,19 +3,19 @@
 // (backward.cuh) with sin(k phi) from the SAME Reinsch chains as the forward
 // kernel instead of one sinpif per oscillator: 10 packed instructions per sample
 // pair and harmonic pair, plus a 16-value transposing warp reduction per 8
-// harmonics.  Tiling, frame records and the phase prefix are those of
-// harmonic_v3.cuh.  Every element of G0 / G1 is written (zeros above the live
+// harmonics.  Tiling, frame records and the phase prefix are those of the third
+// forward generation (profiles/experiments/harmonic_v3.cuh.txt).  Every element of G0 / G1 is written (zeros above the live
 // count), so the caller needs no memset.
 #pragma once
 #include "backward.cuh"
-#include "harmonic_v3.cuh"
+#include "harmonic_common.cuh"
 
 namespace ddsp {
 namespace hb2 {
 
-using hv3::FrameRec;
-using hv3::NT;
-using hv3::NW;
+using hcm::FrameRec;
+constexpr int NW = hcm::kBwdWarps;
+constexpr int NT = NW * 32;
 
 struct Smem {
   size_t off_tab, off_red, off_warp, warp_stride, total;
@@ -46,7 +46,7 @@ struct Chain {
 __device__ __forceinline__ void chain_seed(Chain& c, uint32_t p,
                                            const float2* __restrict__ tab) {
   hcm::Osc o;
-  hv3::osc_seed(o, p, tab);
+  hcm::osc_seed(o, p, tab);
   c.S = o.v;
   c.sigma = o.sigma;
   c.Dd = o.d;

@@ -2,7 +2,7 @@
 // helpers, the 256-entry sin / cos table, the 64-bit fixed-point phase, the
 // per-sample oscillator state (two Reinsch chains over the harmonics, odd / even,
 // in one f32x2), the exact per-oscillator slow path for f0 < 1 Hz, and the
-// get_controls rows for wide harmonic distributions.  Used by harmonic_v3.cuh
+// get_controls rows for wide harmonic distributions.  Used by harmonic_v4.cuh
 // (forward), harmonic_bwd2.cuh / backward.cuh (backward).
 //
 // Derivations (closed-form phase, Reinsch recurrence, per-row accumulators,
@@ -128,6 +128,41 @@ __device__ __forceinline__ float osc_finish(const Osc& st, float w0, float w1) {
   const float r1 = fmaf(st.sigma, st.a1o.x + st.a1o.y, st.a1e.x + st.a1e.y);
   return fmaf(r1, w1, r0 * w0);
 }
+
+// Frame record and oscillator seed of the (odd, even)-chain layout: the backward
+// kernel (harmonic_bwd2.cuh) keeps the third forward generation's records
+// (profiles/experiments/harmonic_v3.cuh.txt); the forward kernel is harmonic_v4.cuh.
+constexpr int kBwdWarps = 4;     // warps per CTA of the backward kernel
+struct __align__(16) FrameRec {
+  unsigned long long P, A;       // P carries the +2^31 rounding offset
+  unsigned long long D;
+  int kca, kcb;                  // live counts at r = 0 / r = hop-1; kca < 0: exact path
+  float f_lo, f_hi, amp0, amp1;
+};
+static_assert(sizeof(FrameRec) == 48, "FrameRec must be three 16-byte words");
+
+// osc_init without zeroing the accumulators.
+__device__ __forceinline__ void osc_seed(Osc& st, uint32_t p,
+                                         const float2* __restrict__ tab) {
+  const uint32_t i = (p + (1u << (31 - kSinTabBits))) >> (32 - kSinTabBits);
+  const int r = (int)(p - (i << (32 - kSinTabBits)));
+  const float2 t = tab[i & (kSinTab - 1)];
+  const float eps = (float)r * 1.4629180792671596e-9f;           // 2 pi / 2^32
+  const float e2 = eps * eps;
+  const float ce = fmaf(e2, -0.5f, 1.0f);
+  const float se = eps * fmaf(e2, -0.16666667f, 1.0f);
+  const float s1 = fmaf(t.y, se, t.x * ce);
+  const float c1 = fmaf(-t.x, se, t.y * ce);
+  const float ss = s1 * s1, cc = c1 * c1;
+  const bool flip = ss > cc;                                     // cos(2 phi) < 0
+  const float s2 = (s1 + s1) * c1;                               // sin(2 phi)
+  const float na = -4.0f * fminf(ss, cc);
+  st.v = make_float2(s1, s2);
+  st.d = make_float2(flip ? 0.0f : s1 + s1, s2);
+  st.na = make_float2(na, na);
+  st.sigma = flip ? -1.0f : 1.0f;
+}
+
 
 // Harmonic.get_controls for up to four rows (r0 .. r0+3 of this warp's block) in
 // shared memory, 8 lanes per row: exp_sigmoid on the live prefix, zeros above it,

@@ -32,7 +32,7 @@ namespace ddsp {
 namespace hv4 {
 
 #ifndef DDSP_HV4_NW
-#define DDSP_HV4_NW 4
+#define DDSP_HV4_NW 1
 #endif
 constexpr int NW = DDSP_HV4_NW;  // warps per CTA
 constexpr int NT = NW * 32;
@@ -41,7 +41,7 @@ constexpr int NT = NW * 32;
 #define DDSP_HV4_PHASE_F64 0
 #endif
 #ifndef DDSP_HV4_MIN_CTAS
-#define DDSP_HV4_MIN_CTAS 6
+#define DDSP_HV4_MIN_CTAS (24 / DDSP_HV4_NW)
 #endif
 
 // 2^32 * (phase + 2^-9 turn): the table index is the top byte of the ROUNDED-UP
@@ -449,7 +449,7 @@ harmonic_v4_kernel(HarmonicParams p, int use_tma, int FW) {
 #pragma unroll
   for (int u = 0; u < TPT; ++u) tab[u] = hcm::g_sincos256[tid + u * NT];
   double part = 0.0;
-  if ((reinterpret_cast<uintptr_t>(f0b) & 15) == 0) {   // i0 is a multiple of 4
+  if ((reinterpret_cast<uintptr_t>(f0b) & 15) == 0) {
     const float4* f4 = reinterpret_cast<const float4*>(f0b);
     const int n4 = i0 >> 2;
     float4 v[4];
@@ -464,9 +464,11 @@ harmonic_v4_kernel(HarmonicParams p, int use_tma, int FW) {
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       v[u] = (j + u * NT < n4) ? f4[j + u * NT] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float tail = (tid < (i0 & 3)) ? f0b[4 * n4 + tid] : 0.f;   // i0 % 4 frames
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       part += ((double)v[u].x + (double)v[u].y) + ((double)v[u].z + (double)v[u].w);
+    part += (double)tail;
   } else {
 #pragma unroll 4
     for (int j = tid; j < i0; j += NT) part += (double)f0b[j];
@@ -680,10 +682,13 @@ inline int launch_harmonic_v4(HarmonicParams p, cudaStream_t st) {
   using namespace hv4;
   p.Kp = (p.K + 3) & ~3;
   static const int env_fw = [] { const char* e = getenv("DDSP_B200_HARM_FW"); return e ? atoi(e) : 0; }();
-  int FW = 8;     // 32-frame tiles: measured 302 us per B=256 decoder step against 306 for 64-frame tiles
-  const long long want_ctas = 8ll * kNumSMs;
-  while (FW > 4 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < want_ctas) FW >>= 1;
-  while (FW > 1 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < kNumSMs) FW >>= 1;
+  // One warp per CTA and 11 frames per warp (12 rows = three get_controls passes):
+  // measured 295 us per B=256 decoder step against 301 for four warps x 8 frames
+  // and 306 for four warps x 16.  Small grids shrink the tile until every SM has one.
+  int FW = (NW == 1) ? 11 : 8;
+  const long long want_ctas = 8ll * kNumSMs * (4 / NW);        // 32 warps per SM
+  while (FW > 4 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < want_ctas) FW = (FW + 1) >> 1;
+  while (FW > 1 && (long long)p.B * ((p.F + FW * NW - 1) / (FW * NW)) < kNumSMs) FW = (FW + 1) >> 1;
   if (env_fw > 0) FW = std::min(32, env_fw);
   FW = std::max(1, std::min(FW, (p.F + NW - 1) / NW));
   while (FW > 1 && smem_layout(FW, p.Kp, p.hop).total > 64 * 1024) FW = (FW + 1) / 2;

@@ -56,7 +56,13 @@ constexpr int RING = 32 * SLOTS;
 constexpr int THREADS = 32 * (CONS_WARPS + PROD_WARPS);
 // NW = 16 only: 640 threads launch with 96 registers each; the consumers (256
 // threads) grow to CONS_REGS out of what the producers (384 threads) give back.
-constexpr int CONS_REGS = (NW == 16) ? 144 : 0, PROD_REGS = 64;
+#ifndef DDSP_NR_PROD_REGS
+#define DDSP_NR_PROD_REGS 64
+#endif
+#ifndef DDSP_NR_CONS_REGS
+#define DDSP_NR_CONS_REGS 144
+#endif
+constexpr int CONS_REGS = (NW == 16) ? DDSP_NR_CONS_REGS : 0, PROD_REGS = DDSP_NR_PROD_REGS;
 constexpr int HPAD = 2, HS = 134, XS = 66, MS = 65;   // row strides (floats)
 constexpr int NQ = FRAME / 4;
 
@@ -99,6 +105,21 @@ __device__ __forceinline__ void mbar_arrive_n(void* bar, int n) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                "r"(n)
                : "memory");
+}
+
+// Shared-memory loads the scheduler may neither merge nor reorder (software
+// pipelines that need several loads in flight with distinct destinations).
+__device__ __forceinline__ float4 lds128v(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float lds32v(const float* p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  return v;
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c,
@@ -471,31 +492,51 @@ noise_ring_kernel(Params p) {
         float e8 = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) aE[c] = aO[c] = make_float2(0.f, 0.f);
-#pragma unroll 4
-        for (int k = 0; k < NO; ++k) {
-          const float me = mrow[2 * k], mo = mrow[2 * k + 1];
-          const float4* tE = reinterpret_cast<const float4*>(sm.te + k * QP + n0);
-          const float4* tO = reinterpret_cast<const float4*>(sm.to + k * QP + n0);
-          const float4 e0 = tE[0], e1 = tE[1], o0 = tO[0], o1 = tO[1];
-          aE[0] = nf_ffma2(me, make_float2(e0.x, e0.y), aE[0]);
-          aE[1] = nf_ffma2(me, make_float2(e0.z, e0.w), aE[1]);
-          aE[2] = nf_ffma2(me, make_float2(e1.x, e1.y), aE[2]);
-          aE[3] = nf_ffma2(me, make_float2(e1.z, e1.w), aE[3]);
-          aO[0] = nf_ffma2(mo, make_float2(o0.x, o0.y), aO[0]);
-          aO[1] = nf_ffma2(mo, make_float2(o0.z, o0.w), aO[1]);
-          aO[2] = nf_ffma2(mo, make_float2(o1.x, o1.y), aO[2]);
-          aO[3] = nf_ffma2(mo, make_float2(o1.z, o1.w), aO[3]);
-          if (iw == 3) e8 = fmaf(me, sm.te[k * QP + Q], e8);
+        // Software-pipelined over k, two register sets: the loads of term k + 1
+        // are in flight while term k is multiplied.  (Left to ptxas, every
+        // LDS.128 of this loop landed in the same four registers - one load in
+        // flight per warp, the loop ran at shared-memory latency: 35 % of the
+        // producers' stall samples were short-scoreboard waits.)  The loads are
+        // volatile asm so that their order and their distinct destinations stay.
+        struct Term { float me, mo; float4 e0, e1, o0, o1; };
+        auto load_term = [&](Term& t, int k) {
+          const float* pm = mrow + 2 * k;
+          const float* pe = sm.te + k * QP + n0;
+          const float* po = sm.to + k * QP + n0;
+          t.me = lds32v(pm);
+          t.mo = lds32v(pm + 1);
+          t.e0 = lds128v(pe); t.e1 = lds128v(pe + 4);
+          t.o0 = lds128v(po); t.o1 = lds128v(po + 4);
+        };
+        auto mac_term = [&](const Term& t, int k) {
+          aE[0] = nf_ffma2(t.me, make_float2(t.e0.x, t.e0.y), aE[0]);
+          aE[1] = nf_ffma2(t.me, make_float2(t.e0.z, t.e0.w), aE[1]);
+          aE[2] = nf_ffma2(t.me, make_float2(t.e1.x, t.e1.y), aE[2]);
+          aE[3] = nf_ffma2(t.me, make_float2(t.e1.z, t.e1.w), aE[3]);
+          aO[0] = nf_ffma2(t.mo, make_float2(t.o0.x, t.o0.y), aO[0]);
+          aO[1] = nf_ffma2(t.mo, make_float2(t.o0.z, t.o0.w), aO[1]);
+          aO[2] = nf_ffma2(t.mo, make_float2(t.o1.x, t.o1.y), aO[2]);
+          aO[3] = nf_ffma2(t.mo, make_float2(t.o1.z, t.o1.w), aO[3]);
+          if (iw == 3) e8 = fmaf(t.me, sm.te[k * QP + Q], e8);
+        };
+        Term tA, tB;
+        load_term(tA, 0);
+#pragma unroll 1
+        for (int k = 0; k < NO; k += 2) {
+          load_term(tB, k + 1);
+          mac_term(tA, k);
+          // k + 2 = 32 is the last, even-only term: its odd operands are read
+          // (row 32 of `to` runs into `win`, mrow[65] into the next row / the pad)
+          // and never used
+          load_term(tA, k + 2);
+          mac_term(tB, k + 1);
         }
         {
-          const float me = mrow[2 * NO];               // k = 32: even terms only
-          const float4* tE = reinterpret_cast<const float4*>(sm.te + NO * QP + n0);
-          const float4 e0 = tE[0], e1 = tE[1];
-          aE[0] = nf_ffma2(me, make_float2(e0.x, e0.y), aE[0]);
-          aE[1] = nf_ffma2(me, make_float2(e0.z, e0.w), aE[1]);
-          aE[2] = nf_ffma2(me, make_float2(e1.x, e1.y), aE[2]);
-          aE[3] = nf_ffma2(me, make_float2(e1.z, e1.w), aE[3]);
-          if (iw == 3) e8 = fmaf(me, sm.te[NO * QP + Q], e8);
+          aE[0] = nf_ffma2(tA.me, make_float2(tA.e0.x, tA.e0.y), aE[0]);
+          aE[1] = nf_ffma2(tA.me, make_float2(tA.e0.z, tA.e0.w), aE[1]);
+          aE[2] = nf_ffma2(tA.me, make_float2(tA.e1.x, tA.e1.y), aE[2]);
+          aE[3] = nf_ffma2(tA.me, make_float2(tA.e1.z, tA.e1.w), aE[3]);
+          if (iw == 3) e8 = fmaf(tA.me, sm.te[NO * QP + Q], e8);
         }
         named_bar(bar_id, PT);     // the group is done reading the rows
         if (nxt.ok) roff = prefetch(nxt.sg, nxt.tau);
@@ -504,15 +545,36 @@ noise_ring_kernel(Params p) {
                             aE[2].x, aE[2].y, aE[3].x, aE[3].y};
         const float O[8] = {aO[0].x, aO[0].y, aO[1].x, aO[1].y,
                             aO[2].x, aO[2].y, aO[3].x, aO[3].y};
+        // window: two 16-byte loads per half (the periodic Hann window is symmetric
+        // about tap 64: win[64 - n] == win[64 + n], win[128 - n] == win[n]); taps
+        // leave as 8-byte stores where the pair is this lane's own
+        const float4 wp0 = *reinterpret_cast<const float4*>(sm.win + SHIFT + n0);
+        const float4 wp1 = *reinterpret_cast<const float4*>(sm.win + SHIFT + n0 + 4);
+        const float4 wm0 = *reinterpret_cast<const float4*>(sm.win + n0);
+        const float4 wm1 = *reinterpret_cast<const float4*>(sm.win + n0 + 4);
+        const float WP[8] = {wp0.x, wp0.y, wp0.z, wp0.w, wp1.x, wp1.y, wp1.z, wp1.w};
+        const float WM[8] = {wm0.x, wm0.y, wm0.z, wm0.w, wm1.x, wm1.y, wm1.z, wm1.w};
+        float vp[8], vm[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const int n = n0 + c;
-          const float hp = row_ok ? E[c] + O[c] : 0.f;   // |offset| = n
-          const float hm = row_ok ? E[c] - O[c] : 0.f;   // |offset| = 64 - n
-          hr[SHIFT + n] = sm.win[SHIFT + n] * hp;
-          if (n != 0) hr[SHIFT - n] = sm.win[SHIFT - n] * hp;
-          if (n != 0) hr[S - n] = sm.win[S - n] * hm;  // tap 64 + (64 - n)
-          hr[n] = sm.win[n] * hm;                      // tap 64 - (64 - n)
+          vp[c] = row_ok ? WP[c] * (E[c] + O[c]) : 0.f;   // |offset| = n
+          vm[c] = row_ok ? WM[c] * (E[c] - O[c]) : 0.f;   // |offset| = 64 - n
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {                 // taps 64 + n and 64 - (64 - n)
+          *reinterpret_cast<float2*>(hr + SHIFT + n0 + c) = make_float2(vp[c], vp[c + 1]);
+          *reinterpret_cast<float2*>(hr + n0 + c) = make_float2(vm[c], vm[c + 1]);
+        }
+#pragma unroll
+        for (int c = 1; c < 7; c += 2) {                 // taps 64 - n and 128 - n, descending
+          *reinterpret_cast<float2*>(hr + SHIFT - n0 - c - 1) = make_float2(vp[c + 1], vp[c]);
+          *reinterpret_cast<float2*>(hr + S - n0 - c - 1) = make_float2(vm[c + 1], vm[c]);
+        }
+        hr[SHIFT - n0 - 7] = vp[7];
+        hr[S - n0 - 7] = vm[7];
+        if (n0 != 0) {
+          hr[SHIFT - n0] = vp[0];
+          hr[S - n0] = vm[0];                            // tap 64 + (64 - n)
         }
         if (iw == 3) {                                 // n = 32: O[32] = 0
           if (!row_ok) e8 = 0.f;

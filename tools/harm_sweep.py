@@ -7,7 +7,7 @@ from ddsp_b200 import _lib, core
 from tests.util import synth_inputs
 
 lib = _lib.load()
-tag = 'harmonic_v3 FW=%s' % os.environ.get('DDSP_B200_HARM_FW', 'auto')
+tag = 'harmonic_v4 FW=%s' % os.environ.get('DDSP_B200_HARM_FW', 'auto')
 for B in (256, 32):
   inp = synth_inputs(B, 1000, 100, 65, 64000, seed=1234)
   f = {k: torch.from_numpy(inp[k]).cuda() for k in ['amps', 'harmonic_distribution', 'f0_hz', 'noise_magnitudes']}

@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'ddsp_b200', 'libddsp_b200.so')
 KERNELS = {
-    'harmonic_v3': 'harmonic_v3_kernelILb1ELi64',
+    'harmonic_v4': 'harmonic_v4_kernelILb1ELi64',
     'noise_ring': 'noise_ring_kernel',
     'harmonic_backward2': 'harmonic_backward2_kernelILb1',
     'lc_mac_ifft': 'lc_mac_ifft',
