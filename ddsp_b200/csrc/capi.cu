@@ -1141,4 +1141,14 @@ int ddsp_b200_spectral_l1(const float* stft_target, const float* stft_value,
   return 0;
 }
 
+#ifdef DDSP_NR_TIMING
+// measurement builds only (tools/noise_timing.py): the noise_ring phase counters of
+// the last launch, [148 CTAs][32 warps][8 phases] cycles
+int ddsp_b200_debug_noise_timing(unsigned* host_out) {
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, ddsp::nr_::g_nr_timing,
+                                       sizeof(unsigned) * kNumSMs * 32 * 8);
+  return e == cudaSuccess ? 0 : DDSP_B200_E_CUDA;
+}
+#endif
+
 }  // extern "C"

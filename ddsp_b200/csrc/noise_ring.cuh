@@ -45,13 +45,27 @@ constexpr int NE = 33, NO = 32, SHIFT = 64;
 // FFMA2) were both measured: 343 vs 357 us per B=256 decoder step.  The FIR is
 // bound by the FMA pipe either way - FFMA2 with a broadcast scalar operand issues
 // every 2.4 cycles per sub-partition, not 2 (tools/microbench2.cu).
-constexpr int NW = 16;
+#ifndef DDSP_NR_NW
+#define DDSP_NR_NW 16
+#endif
+constexpr int NW = DDSP_NR_NW;
 constexpr int UPT = FRAME / (2 * NW);              // units per 64-sample frame
-constexpr int CONS_WARPS = 8, PROD_GROUPS = 3, PROD_WARPS = 4 * PROD_GROUPS;
+#ifndef DDSP_NR_PHILOX_EARLY
+#define DDSP_NR_PHILOX_EARLY 0
+#endif
+#ifndef DDSP_NR_PROD_GROUPS
+#define DDSP_NR_PROD_GROUPS 3
+#endif
+#ifndef DDSP_NR_MAX_SLOTS
+#define DDSP_NR_MAX_SLOTS 7
+#endif
+constexpr int CONS_WARPS = 8, PROD_GROUPS = DDSP_NR_PROD_GROUPS, PROD_WARPS = 4 * PROD_GROUPS;
 constexpr int NTG = CONS_WARPS / UPT;              // consumption tiles in flight
+static_assert((NTG & (NTG - 1)) == 0, "tile groups: a power of two");
 // 32-row slots in the ring: the consumers hold NTG + 1 of them, each producer
-// group fills one more - as far as 227 KB of shared memory go (7 slots)
-constexpr int SLOTS = (NTG + 1 + PROD_GROUPS) < 7 ? (NTG + 1 + PROD_GROUPS) : 7;
+// group fills one more - as far as 227 KB of shared memory go (7 slots with three
+// raw-magnitude staging buffers, 8 with two)
+constexpr int SLOTS = DDSP_NR_MAX_SLOTS;
 constexpr int RING = 32 * SLOTS;
 constexpr int THREADS = 32 * (CONS_WARPS + PROD_WARPS);
 // NW = 16 only: 640 threads launch with 96 registers each; the consumers (256
@@ -66,7 +80,26 @@ constexpr int CONS_REGS = (NW == 16) ? DDSP_NR_CONS_REGS : 0, PROD_REGS = DDSP_N
 constexpr int HPAD = 2, HS = 134, XS = 66, MS = 65;   // row strides (floats)
 constexpr int NQ = FRAME / 4;
 
+// -DDDSP_NR_TIMING: per-warp cycle counters by phase (tools/noise_timing.py reads
+// them back through ddsp_b200_debug_noise_timing); measurement builds only.
+#ifdef DDSP_NR_TIMING
+#define NR_TIMING_DECL unsigned tprev__ = (unsigned)clock()
+#define NR_LAP(i)                                                        \
+  do {                                                                   \
+    const unsigned n__ = (unsigned)clock();                              \
+    if (lane == 0) sm.tacc[warp * 8 + (i)] += n__ - tprev__;             \
+    tprev__ = n__;                                                       \
+  } while (0)
+__device__ unsigned g_nr_timing[kNumSMs * 32 * 8];
+#else
+#define NR_TIMING_DECL
+#define NR_LAP(i)
+#endif
+
 struct Smem {
+#ifdef DDSP_NR_TIMING
+  unsigned tacc[32 * 8];
+#endif
   float te[NE * QP];
   float to[NO * QP];
   float win[S];
@@ -282,6 +315,9 @@ noise_ring_kernel(Params p) {
     sm.win[j] = 0.5f - 0.5f * cospif(2.0f * (float)j / (float)S0);   // core.py:1498,1515
   for (int e = tid; e < RING * HS; e += THREADS) sm.h[e] = 0.f;
   for (int e = tid; e < RING * XS; e += THREADS) sm.x[e] = 0.f;
+#ifdef DDSP_NR_TIMING
+  for (int e = tid; e < 32 * 8; e += THREADS) sm.tacc[e] = 0;
+#endif
   if (tid == 0) {
     for (int i = 0; i < SLOTS; ++i) {
       mbar_init(&sm.full[i], 4);
@@ -303,11 +339,13 @@ noise_ring_kernel(Params p) {
     const int tg = warp / UPT, unit = warp % UPT;      // tile group, unit of the tile
     long long g = g_lo;
     Seg sg;
-    int pbase = 0, ct = 0;
+    int pbase = 0, ct = 0;                   // ct: consumption tiles before this segment
     bool dep_done = false;
+    NR_TIMING_DECL;
     while (next_seg(g, g_hi, p.F, sg)) {
-      for (int t = 0; t < sg.nC; ++t, ++ct) {
-        if ((ct % NTG) != tg) continue;
+      // tiles ct + t of the CTA go round-robin over the tile groups
+      for (int t = (tg - ct) & (NTG - 1); t < sg.nC; t += NTG) {
+        NR_LAP(3);
         // rows of this tile live in production tiles t and t+1 of the segment
         // (two producer groups finish tiles out of order: wait for both)
         {
@@ -315,6 +353,7 @@ noise_ring_kernel(Params p) {
           mbar_wait(&sm.full[P0 % SLOTS], (P0 / SLOTS) & 1);
           mbar_wait(&sm.full[P1 % SLOTS], (P1 / SLOTS) & 1);
         }
+        NR_LAP(0);
         const int q_rel = 32 * t + lane;                // output frame, relative
         // lanes past the end of the segment redo its last frame (and store
         // nothing): they must not wander into rows nobody produced
@@ -332,6 +371,7 @@ noise_ring_kernel(Params p) {
         if (unit == 0)
           a.A[0].x = fmaf(xrow(rho - 2)[63], hrow(rho - 2)[127], a.A[0].x);
         __syncwarp();
+        NR_LAP(1);
         if (lane == 0) {
           // release the slots: a production tile is read by consumption tiles
           // tau-1 and tau (UPT warps each); a lone reader arrives twice.
@@ -382,7 +422,9 @@ noise_ring_kernel(Params p) {
             }
           }
         }
+        NR_LAP(2);
       }
+      ct += sg.nC;
       pbase += sg.nP;
     }
   } else {
@@ -458,7 +500,9 @@ noise_ring_kernel(Params p) {
     int roff = 0;
     if (cur.ok) roff = prefetch(cur.sg, cur.tau);
     int n_mine = 0;                                   // tiles this group has staged
+    NR_TIMING_DECL;
     while (cur.ok) {
+      NR_LAP(7);
       It nxt = cur;
       for (int i = 0; i < PROD_GROUPS && nxt.ok; ++i) it_next(nxt);
       const Seg& sg = cur.sg;
@@ -467,6 +511,7 @@ noise_ring_kernel(Params p) {
       // A. exp_sigmoid in place on the raw rows (synths.py:176-177); rows of frames
       //    outside [0, F) hold nothing and are forced to zero taps below
       mbar_wait(rawbar, n_mine & 1);
+      NR_LAP(0);
       const bool row_ok = (jb + lane >= 0) && (jb + lane < p.F);
       const float* mrow = row_ok ? s_raw + roff + lane * NB : s_raw;
       if (p.raw && row_ok) {
@@ -482,8 +527,20 @@ noise_ring_kernel(Params p) {
       }
       named_bar(bar_id, PT);       // rows complete
       ++n_mine;
-      // wait until the consumers have drained this slot
+      NR_LAP(1);
+#ifdef DDSP_NR_EARLY_EMPTY_WAIT
       if (P >= SLOTS) mbar_wait(&sm.empty[slot], ((P / SLOTS) - 1) & 1);
+#endif
+      // the tile's noise rows (C. below): 512 quads, 128 per warp
+      const float* nzb = p.noise ? p.noise + (size_t)sg.b * p.N : nullptr;
+      const uint32_t item = (uint32_t)(sg.b + p.item_base);
+      const long long p_lo = (long long)jb * FRAME;
+      const bool interior = (jb >= 0) && (jb + 32 <= p.F) &&
+                            (p_lo + 32ll * FRAME <= p.N) && !nzb;
+      constexpr int PER = 32 * NQ / 4;                 // 128 quads per warp
+#if DDSP_NR_PHILOX_EARLY
+      float4 nzq[PER / 32];
+#endif
       // B. both half-size cosine sums of 8 columns (9 for the last block):
       //    h0[n] = E[n] + O[n], h0[64 - n] = E[n] - O[n]   
       {
@@ -538,8 +595,29 @@ noise_ring_kernel(Params p) {
           aE[3] = nf_ffma2(tA.me, make_float2(tA.e1.z, tA.e1.w), aE[3]);
           if (iw == 3) e8 = fmaf(tA.me, sm.te[NO * QP + Q], e8);
         }
+        NR_LAP(3);
         named_bar(bar_id, PT);     // the group is done reading the rows
         if (nxt.ok) roff = prefetch(nxt.sg, nxt.tau);
+        NR_LAP(4);
+        // Only now does the group need its ring slot: the cosine sums above live in
+        // registers.  (The wait used to sit in front of them: with two free slots for
+        // three groups, a tile took ~8300 cycles from "slot free" to "full" - 1.7 tile
+        // periods - and consumers waited on `full` 8.6 % of their time while producers
+        // waited on `empty` 32 % of theirs; tools/noise_timing.py.)
+#if DDSP_NR_PHILOX_EARLY
+        // interior tiles: the noise quads are drawn into registers as well, so that
+        // all that is left to do once the slot is free are stores
+        if (interior) {
+          const uint32_t qbase = (uint32_t)(p_lo >> 2);
+#pragma unroll
+          for (int it = 0; it < PER / 32; ++it)
+            nzq[it] = noise4(qbase + (uint32_t)(iw * PER + it * 32 + lane), item, p.seed, p.offset);
+        }
+#endif
+#ifndef DDSP_NR_EARLY_EMPTY_WAIT
+        if (P >= SLOTS) mbar_wait(&sm.empty[slot], ((P / SLOTS) - 1) & 1);
+#endif
+        NR_LAP(2);
         float* hr = sm.h + (slot * 32 + lane) * HS + HPAD;
         const float E[8] = {aE[0].x, aE[0].y, aE[1].x, aE[1].y,
                             aE[2].x, aE[2].y, aE[3].x, aE[3].y};
@@ -582,22 +660,23 @@ noise_ring_kernel(Params p) {
           hr[SHIFT - Q] = sm.win[SHIFT - Q] * e8;
         }
       }
-      // C. the tile's noise rows: 512 quads, 128 per warp
+      NR_LAP(5);
+      // C. the tile's noise rows
       {
-        const float* nzb = p.noise ? p.noise + (size_t)sg.b * p.N : nullptr;
-        const uint32_t item = (uint32_t)(sg.b + p.item_base);
         float* xs = sm.x + slot * 32 * XS;
-        const long long p_lo = (long long)jb * FRAME;
-        const bool interior = (jb >= 0) && (jb + 32 <= p.F) &&
-                              (p_lo + 32ll * FRAME <= p.N) && !nzb;
-        constexpr int PER = 32 * NQ / 4;               // 128 quads per warp
         if (interior) {
+#if !DDSP_NR_PHILOX_EARLY
           const uint32_t qbase = (uint32_t)(p_lo >> 2);
+#endif
 #pragma unroll
           for (int it = 0; it < PER / 32; ++it) {
             const int e = iw * PER + it * 32 + lane;
             const int r = e >> 4, qd = e & 15;
+#if DDSP_NR_PHILOX_EARLY
+            const float4 v = nzq[it];
+#else
             const float4 v = noise4(qbase + (uint32_t)e, item, p.seed, p.offset);
+#endif
             float2* d = reinterpret_cast<float2*>(xs + r * XS + 4 * qd);
             d[0] = make_float2(v.x, v.y);
             d[1] = make_float2(v.z, v.w);
@@ -629,9 +708,15 @@ noise_ring_kernel(Params p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.full[slot]);
+      NR_LAP(6);
       cur = nxt;
     }
   }
+#ifdef DDSP_NR_TIMING
+  __syncthreads();
+  for (int e = tid; e < 32 * 8; e += THREADS)
+    g_nr_timing[blockIdx.x * 32 * 8 + e] = sm.tacc[e];
+#endif
 }
 
 }  // namespace nr_
