@@ -34,9 +34,10 @@
 //     complementary triangles of the (n, i) square; fully unrolled bodies skip the
 //     pairs whose taps are all out of range.
 //   * producers: two groups of 4 warps alternate tiles; a group takes its tile
-//     from raw magnitudes (TMA) through exp_sigmoid, both cosine half-sums (in
-//     registers as FFMA2, no exchange) and the windowed taps to the Philox rows,
-//     and asks for its ring slot only when the sums are done.
+//     from raw magnitudes (TMA) through exp_sigmoid, the cosine sums (odd k, and the
+//     even k split once more by quarter-wave symmetry: 1601 MACs per frame instead
+//     of 4225; in registers as FFMA2, no exchange) and the windowed taps to the
+//     Philox rows, and asks for its ring slot only when the sums are done.
 #pragma once
 #include "noise_fused.cuh"
 
@@ -75,14 +76,15 @@ constexpr int RING = 32 * SLOTS;
 constexpr int THREADS = 32 * (CONS_WARPS + PROD_WARPS);
 // NW = 16 only: 512 threads launch with 128 registers each (the whole file); the
 // consumers (256 threads) grow to CONS_REGS out of what the producers (256 threads)
-// give back: CONS_REGS + PROD_REGS <= 256.  (Three groups: 640 threads at 96, 144 /
-// 64.  A split that leaves setmaxnreg.inc short of registers hangs the CTA: 72 / 144
-// with three groups did.)
+// give back: CONS_REGS + PROD_REGS <= 256.  Measured (kernel alone, B = 256): 152 /
+// 104 138.3 us, 168 / 88 135.7 us, 136 / 120 141.1 us.  (Three groups: 640 threads at
+// 96, 144 / 64.  A split that leaves setmaxnreg.inc short of registers hangs the
+// CTA: 72 / 144 with three groups did.)
 #ifndef DDSP_NR_PROD_REGS
-#define DDSP_NR_PROD_REGS 104
+#define DDSP_NR_PROD_REGS 88
 #endif
 #ifndef DDSP_NR_CONS_REGS
-#define DDSP_NR_CONS_REGS 152
+#define DDSP_NR_CONS_REGS 168
 #endif
 static_assert(DDSP_NR_NW != 16 ||
                   8 * DDSP_NR_CONS_REGS + 4 * DDSP_NR_PROD_GROUPS * DDSP_NR_PROD_REGS <= 2048,
@@ -303,9 +305,18 @@ noise_ring_kernel(Params p) {
     sm.te[e] = (n <= Q) ? ck * cospif(2.0f * (float)ph * invS0) : 0.f;
   }
   for (int e = tid; e < NO * QP; e += THREADS) {
-    const int k = e / QP, n = e - k * QP;
-    const int ph = ((2 * k + 1) * n) % S0;
-    sm.to[e] = (n < Q) ? 2.0f * invS0 * cospif(2.0f * (float)ph * invS0) : 0.f;
+    // odd-k table, laid out by producer warp: columns 8 w + c hold n = 4 w + c
+    // (c < 4) and its mirror n = 32 - 4 w - (c - 4) (c >= 4); column 32 holds n = 16
+    const int k = e / QP, col = e - k * QP;
+    int n = -1;
+    if (col < 32) {
+      const int w = col >> 3, c = col & 7;
+      n = (c < 4) ? 4 * w + c : 32 - 4 * w - (c - 4);
+    } else if (col == 32) {
+      n = 16;
+    }
+    const int ph = ((2 * k + 1) * max(n, 0)) % S0;
+    sm.to[e] = (n >= 0) ? 2.0f * invS0 * cospif(2.0f * (float)ph * invS0) : 0.f;
   }
   for (int j = tid; j < S; j += THREADS)
     sm.win[j] = 0.5f - 0.5f * cospif(2.0f * (float)j / (float)S0);   // core.py:1498,1515
@@ -531,113 +542,120 @@ noise_ring_kernel(Params p) {
       const bool interior = (jb >= 0) && (jb + 32 <= p.F) &&
                             (p_lo + 32ll * FRAME <= p.N) && !nzb;
       constexpr int PER = 32 * NQ / 4;                 // 128 quads per warp
-      // B. both half-size cosine sums of 8 columns (9 for the last block):
-      //    h0[n] = E[n] + O[n], h0[64 - n] = E[n] - O[n]   
+      // B. the cosine sums, with the quarter-wave symmetry of the even-k half:
+      //    h0[n] = E[n] + O[n], h0[64 - n] = E[n] - O[n], and, splitting
+      //    the even k = 2 j by the parity of j, E[n] = EE[n] + EO[n], E[32 - n] =
+      //    EE[n] - EO[n]: 289 + 256 + 1056 MACs per frame instead of 1089 + 1024.
+      //    Warp w owns n = 4 w .. 4 w + 3 and their mirrors 32 - n (warp 3 also the
+      //    self-mirrored n = 16, where EO vanishes).
       {
-        const int n0 = 8 * iw;
-        float2 aE[4], aO[4];
-        float e8 = 0.f;
+        const int c0 = 4 * iw;
+        float2 aEE[2], aEO[2], aOa[2], aOb[2];
+        float ee16 = 0.f, o16 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) aE[c] = aO[c] = make_float2(0.f, 0.f);
-        // Software-pipelined over k, two register sets: the loads of term k + 1
-        // are in flight while term k is multiplied.  (Left to ptxas, every
-        // LDS.128 of this loop landed in the same four registers - one load in
-        // flight per warp, the loop ran at shared-memory latency: 35 % of the
-        // producers' stall samples were short-scoreboard waits.)  The loads are
-        // volatile asm so that their order and their distinct destinations stay.
-        struct Term { float me, mo; float4 e0, e1, o0, o1; };
-        auto load_term = [&](Term& t, int k) {
-          const float* pm = mrow + 2 * k;
-          const float* pe = sm.te + k * QP + n0;
-          const float* po = sm.to + k * QP + n0;
-          t.me = lds32v(pm);
-          t.mo = lds32v(pm + 1);
-          t.e0 = lds128v(pe); t.e1 = lds128v(pe + 4);
-          t.o0 = lds128v(po); t.o1 = lds128v(po + 4);
+        for (int c = 0; c < 2; ++c) aEE[c] = aEO[c] = aOa[c] = aOb[c] = make_float2(0.f, 0.f);
+        // Software-pipelined over groups of four k (two register sets: the loads of
+        // group j2 + 1 are in flight while group j2 is multiplied); volatile loads so
+        // that their order and their distinct destinations stay.
+        struct Term { float m0, m1, m2, m3; float4 e0, e1, oa0, ob0, oa1, ob1; };
+        auto load_term = [&](Term& t, int j2) {
+          const float* pm = mrow + 4 * j2;               // k = 4 j2 .. 4 j2 + 3
+          const float* pe = sm.te + (2 * j2) * QP + c0;
+          const float* po = sm.to + (2 * j2) * QP + 8 * iw;
+          t.m0 = lds32v(pm); t.m1 = lds32v(pm + 1);
+          t.m2 = lds32v(pm + 2); t.m3 = lds32v(pm + 3);
+          t.e0 = lds128v(pe); t.e1 = lds128v(pe + QP);
+          t.oa0 = lds128v(po); t.ob0 = lds128v(po + 4);
+          t.oa1 = lds128v(po + QP); t.ob1 = lds128v(po + QP + 4);
         };
-        auto mac_term = [&](const Term& t, int k) {
-          aE[0] = nf_ffma2(t.me, make_float2(t.e0.x, t.e0.y), aE[0]);
-          aE[1] = nf_ffma2(t.me, make_float2(t.e0.z, t.e0.w), aE[1]);
-          aE[2] = nf_ffma2(t.me, make_float2(t.e1.x, t.e1.y), aE[2]);
-          aE[3] = nf_ffma2(t.me, make_float2(t.e1.z, t.e1.w), aE[3]);
-          aO[0] = nf_ffma2(t.mo, make_float2(t.o0.x, t.o0.y), aO[0]);
-          aO[1] = nf_ffma2(t.mo, make_float2(t.o0.z, t.o0.w), aO[1]);
-          aO[2] = nf_ffma2(t.mo, make_float2(t.o1.x, t.o1.y), aO[2]);
-          aO[3] = nf_ffma2(t.mo, make_float2(t.o1.z, t.o1.w), aO[3]);
-          if (iw == 3) e8 = fmaf(t.me, sm.te[k * QP + Q], e8);
+        auto mac_term = [&](const Term& t, int j2) {
+          aEE[0] = nf_ffma2(t.m0, make_float2(t.e0.x, t.e0.y), aEE[0]);
+          aEE[1] = nf_ffma2(t.m0, make_float2(t.e0.z, t.e0.w), aEE[1]);
+          aOa[0] = nf_ffma2(t.m1, make_float2(t.oa0.x, t.oa0.y), aOa[0]);
+          aOa[1] = nf_ffma2(t.m1, make_float2(t.oa0.z, t.oa0.w), aOa[1]);
+          aOb[0] = nf_ffma2(t.m1, make_float2(t.ob0.x, t.ob0.y), aOb[0]);
+          aOb[1] = nf_ffma2(t.m1, make_float2(t.ob0.z, t.ob0.w), aOb[1]);
+          aEO[0] = nf_ffma2(t.m2, make_float2(t.e1.x, t.e1.y), aEO[0]);
+          aEO[1] = nf_ffma2(t.m2, make_float2(t.e1.z, t.e1.w), aEO[1]);
+          aOa[0] = nf_ffma2(t.m3, make_float2(t.oa1.x, t.oa1.y), aOa[0]);
+          aOa[1] = nf_ffma2(t.m3, make_float2(t.oa1.z, t.oa1.w), aOa[1]);
+          aOb[0] = nf_ffma2(t.m3, make_float2(t.ob1.x, t.ob1.y), aOb[0]);
+          aOb[1] = nf_ffma2(t.m3, make_float2(t.ob1.z, t.ob1.w), aOb[1]);
+          if (iw == 3) {
+            ee16 = fmaf(t.m0, sm.te[(2 * j2) * QP + 16], ee16);
+            o16 = fmaf(t.m1, sm.to[(2 * j2) * QP + 32], o16);
+            o16 = fmaf(t.m3, sm.to[(2 * j2 + 1) * QP + 32], o16);
+          }
         };
         Term tA, tB;
         load_term(tA, 0);
 #pragma unroll 1
-        for (int k = 0; k < NO; k += 2) {
-          load_term(tB, k + 1);
-          mac_term(tA, k);
-          // k + 2 = 32 is the last, even-only term: its odd operands are read
-          // (row 32 of `to` runs into `win`, mrow[65] into the next row / the pad)
-          // and never used
-          load_term(tA, k + 2);
-          mac_term(tB, k + 1);
+        for (int j2 = 0; j2 < NO / 2; j2 += 2) {
+          load_term(tB, j2 + 1);
+          mac_term(tA, j2);
+          // j2 + 2 = 16 is k = 64, the last even-even term: the rest of that group is
+          // read (table rows past the end run into the next array, mrow[65 .. 67] into
+          // the next row / the pad) and never used
+          load_term(tA, j2 + 2);
+          mac_term(tB, j2 + 1);
         }
-        {
-          aE[0] = nf_ffma2(tA.me, make_float2(tA.e0.x, tA.e0.y), aE[0]);
-          aE[1] = nf_ffma2(tA.me, make_float2(tA.e0.z, tA.e0.w), aE[1]);
-          aE[2] = nf_ffma2(tA.me, make_float2(tA.e1.x, tA.e1.y), aE[2]);
-          aE[3] = nf_ffma2(tA.me, make_float2(tA.e1.z, tA.e1.w), aE[3]);
-          if (iw == 3) e8 = fmaf(tA.me, sm.te[NO * QP + Q], e8);
-        }
+        aEE[0] = nf_ffma2(tA.m0, make_float2(tA.e0.x, tA.e0.y), aEE[0]);
+        aEE[1] = nf_ffma2(tA.m0, make_float2(tA.e0.z, tA.e0.w), aEE[1]);
+        if (iw == 3) ee16 = fmaf(tA.m0, sm.te[NO * QP + 16], ee16);
         NR_LAP(3);
         named_bar(bar_id, PT);     // the group is done reading the rows
         if (nxt.ok) roff = prefetch(nxt.sg, nxt.tau);
         NR_LAP(4);
-        // Only now does the group need its ring slot: the cosine sums above live in
-        // registers.  (The wait used to sit in front of them: a tile then took ~8300
-        // cycles from "slot free" to "full", 1.7 tile periods, and consumers waited on
-        // `full` 8.6 % of their time while producers waited on `empty` 32 % of theirs;
-        // tools/noise_timing.py.  Drawing the noise rows into registers ahead of the
-        // wait as well was measured: 158 vs 142 us with 64-register producers, no
-        // change with 104.)
+        // Only now does the group need its ring slot: the sums above live in registers.
         if (P >= SLOTS) mbar_wait(&sm.empty[slot], ((P / SLOTS) - 1) & 1);
         NR_LAP(2);
         float* hr = sm.h + (slot * 32 + lane) * HS + HPAD;
-        const float E[8] = {aE[0].x, aE[0].y, aE[1].x, aE[1].y,
-                            aE[2].x, aE[2].y, aE[3].x, aE[3].y};
-        const float O[8] = {aO[0].x, aO[0].y, aO[1].x, aO[1].y,
-                            aO[2].x, aO[2].y, aO[3].x, aO[3].y};
-        // window: two 16-byte loads per half (the periodic Hann window is symmetric
-        // about tap 64: win[64 - n] == win[64 + n], win[128 - n] == win[n]); taps
-        // leave as 8-byte stores where the pair is this lane's own
-        const float4 wp0 = *reinterpret_cast<const float4*>(sm.win + SHIFT + n0);
-        const float4 wp1 = *reinterpret_cast<const float4*>(sm.win + SHIFT + n0 + 4);
-        const float4 wm0 = *reinterpret_cast<const float4*>(sm.win + n0);
-        const float4 wm1 = *reinterpret_cast<const float4*>(sm.win + n0 + 4);
-        const float WP[8] = {wp0.x, wp0.y, wp0.z, wp0.w, wp1.x, wp1.y, wp1.z, wp1.w};
-        const float WM[8] = {wm0.x, wm0.y, wm0.z, wm0.w, wm1.x, wm1.y, wm1.z, wm1.w};
-        float vp[8], vm[8];
+        const float EEv[4] = {aEE[0].x, aEE[0].y, aEE[1].x, aEE[1].y};
+        const float EOv[4] = {aEO[0].x, aEO[0].y, aEO[1].x, aEO[1].y};
+        const float OA[4] = {aOa[0].x, aOa[0].y, aOa[1].x, aOa[1].y};
+        const float OB[4] = {aOb[0].x, aOb[0].y, aOb[1].x, aOb[1].y};
+        // window values as 16-byte loads: the periodic Hann window has win[128 - i] ==
+        // win[i], so the mirrors' win[64 + (32 - n)] = win[32 + n], win[32 - n] = win[96 + n]
+        const float4 wpa4 = *reinterpret_cast<const float4*>(sm.win + SHIFT + c0);
+        const float4 wma4 = *reinterpret_cast<const float4*>(sm.win + c0);
+        const float4 wpb4 = *reinterpret_cast<const float4*>(sm.win + Q + c0);
+        const float4 wmb4 = *reinterpret_cast<const float4*>(sm.win + SHIFT + Q + c0);
+        const float WPA[4] = {wpa4.x, wpa4.y, wpa4.z, wpa4.w}, WMA[4] = {wma4.x, wma4.y, wma4.z, wma4.w};
+        const float WPB[4] = {wpb4.x, wpb4.y, wpb4.z, wpb4.w}, WMB[4] = {wmb4.x, wmb4.y, wmb4.z, wmb4.w};
+        float vpa[4], vma[4], vpb[4], vmb[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          vp[c] = row_ok ? WP[c] * (E[c] + O[c]) : 0.f;   // |offset| = n
-          vm[c] = row_ok ? WM[c] * (E[c] - O[c]) : 0.f;   // |offset| = 64 - n
+        for (int c = 0; c < 4; ++c) {
+          const float Ea = EEv[c] + EOv[c], Eb = EEv[c] - EOv[c];     // E[n], E[32 - n]
+          vpa[c] = row_ok ? WPA[c] * (Ea + OA[c]) : 0.f;   // n:      taps 64 +- n
+          vma[c] = row_ok ? WMA[c] * (Ea - OA[c]) : 0.f;   //         taps n, 128 - n
+          vpb[c] = row_ok ? WPB[c] * (Eb + OB[c]) : 0.f;   // 32 - n: taps 96 - n, 32 + n
+          vmb[c] = row_ok ? WMB[c] * (Eb - OB[c]) : 0.f;   //         taps 32 - n, 96 + n
         }
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {                 // taps 64 + n and 64 - (64 - n)
-          *reinterpret_cast<float2*>(hr + SHIFT + n0 + c) = make_float2(vp[c], vp[c + 1]);
-          *reinterpret_cast<float2*>(hr + n0 + c) = make_float2(vm[c], vm[c + 1]);
-        }
-#pragma unroll
-        for (int c = 1; c < 7; c += 2) {                 // taps 64 - n and 128 - n, descending
-          *reinterpret_cast<float2*>(hr + SHIFT - n0 - c - 1) = make_float2(vp[c + 1], vp[c]);
-          *reinterpret_cast<float2*>(hr + S - n0 - c - 1) = make_float2(vm[c + 1], vm[c]);
-        }
-        hr[SHIFT - n0 - 7] = vp[7];
-        hr[S - n0 - 7] = vm[7];
-        if (n0 != 0) {
-          hr[SHIFT - n0] = vp[0];
-          hr[S - n0] = vm[0];                            // tap 64 + (64 - n)
-        }
-        if (iw == 3) {                                 // n = 32: O[32] = 0
-          if (!row_ok) e8 = 0.f;
-          hr[SHIFT + Q] = sm.win[SHIFT + Q] * e8;
-          hr[SHIFT - Q] = sm.win[SHIFT - Q] * e8;
+        // v[c] to hr[base + c] / hr[base - c]; 8-byte stores where the pair starts even
+        auto st_up = [&](int base, const float* v) {
+          *reinterpret_cast<float2*>(hr + base) = make_float2(v[0], v[1]);
+          *reinterpret_cast<float2*>(hr + base + 2) = make_float2(v[2], v[3]);
+        };
+        auto st_down = [&](int base, const float* v, bool first) {
+          if (first) hr[base] = v[0];
+          *reinterpret_cast<float2*>(hr + base - 2) = make_float2(v[2], v[1]);
+          hr[base - 3] = v[3];
+        };
+        st_up(SHIFT + c0, vpa);                          // 64 + n
+        st_down(SHIFT - c0, vpa, true);                  // 64 - n
+        st_up(c0, vma);                                  // n
+        st_down(S - c0, vma, c0 != 0);                   // 128 - n (tap 128 does not exist)
+        st_down(SHIFT + Q - c0, vpb, true);              // 64 + (32 - n)
+        st_up(Q + c0, vpb);                              // 64 - (32 - n)
+        st_down(Q - c0, vmb, true);                      // 32 - n
+        st_up(SHIFT + Q + c0, vmb);                      // 128 - (32 - n)
+        if (iw == 3) {                                   // n = 16
+          const float vp16 = row_ok ? sm.win[SHIFT + 16] * (ee16 + o16) : 0.f;
+          const float vm16 = row_ok ? sm.win[16] * (ee16 - o16) : 0.f;
+          hr[SHIFT + 16] = vp16;
+          hr[SHIFT - 16] = vp16;
+          hr[16] = vm16;
+          hr[S - 16] = vm16;
         }
       }
       NR_LAP(5);

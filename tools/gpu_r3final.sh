@@ -1,7 +1,7 @@
 #!/bin/bash
 # Validation visit: bench lines first (decoder, configs[3]), ncu launch list of the bench command, one full
 # capture of the two decoder kernels, noise_ring phase counters, then the whole GPU test suite.
-O=gpurun_out; mkdir -p $O; T=r3f
+O=gpurun_out; mkdir -p $O; T=r3g
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/${T}_gpu.txt 2>&1
 timeout 240 python bench.py > $O/${T}_bench_n1.json 2> $O/${T}_bench_n1.err; echo "bench rc=$?"; cut -c1-400 $O/${T}_bench_n1.json
 timeout 150 python bench.py --config c4 > $O/${T}_bench_c4.json 2> $O/${T}_bench_c4.err; echo "c4 rc=$?"; cut -c1-300 $O/${T}_bench_c4.json
@@ -10,3 +10,4 @@ timeout 150 ncu --set full --clock-control none --import-source on -k regex:'har
 timeout 60 python tools/noise_timing.py tools/variants/lib_T.so 256 > $O/${T}_timing.log 2>&1; cat $O/${T}_timing.log
 timeout 500 python -m pytest tests -m gpu -q -x --timeout 90 > $O/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${T}_pytest.log
 tail -n 4 $O/${T}_pytest.log
+timeout 90 python tools/variant_time.py 256 tools/variants/lib_final.so tools/variants/lib_R176.so tools/variants/lib_R160.so tools/variants/lib_final.so > $O/${T}_regsplit.log 2>&1; cat $O/${T}_regsplit.log
