@@ -284,6 +284,71 @@ def test_direct_form_fir_equals_fft_convolve():
   assert np.abs(flat[:, 2:] - 0.7 * noise[:, :-2]).max() < 1e-12
 
 
+def test_quarter_wave_cosine_sums_equal_the_impulse_response():
+  """The identities noise_ring's producers rest on (csrc/noise_ring.cuh, section B),
+  restated in NumPy with the kernel's own table layout and tap placement: with
+  m_k the 65 magnitudes, h0 = irfft(m) splits into even-k / odd-k cosine sums
+  (h0[n] = E[n] + O[n], h0[64 - n] = E[n] - O[n]) and the even-k half once more
+  about n = 16 (E[n] = EE[n] + EO[n], E[32 - n] = EE[n] - EO[n]); every one of
+  the 128 windowed taps is written, tap 128 never (core.py:1476-1519)."""
+  nb, S, Q, QP, shift = 65, 128, 32, 36, 64
+  rng = np.random.default_rng(0)
+  m = rng.uniform(0.0, 2.0, size=nb)
+  te = np.zeros((33, QP))
+  to = np.zeros((32, QP))
+  for k in range(33):
+    ck = (1.0 / S) if k in (0, 32) else 2.0 / S
+    for n in range(Q + 1):
+      te[k, n] = ck * np.cos(2.0 * np.pi * ((2 * k * n) % S) / S)
+  for k in range(32):                       # odd-k table, per producer warp
+    for col in range(33):
+      w, c = col >> 3, col & 7
+      n = 16 if col == 32 else (4 * w + c if c < 4 else 32 - 4 * w - (c - 4))
+      to[k, col] = 2.0 / S * np.cos(2.0 * np.pi * (((2 * k + 1) * n) % S) / S)
+  win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(S) / S)
+  hr = np.full(S + 4, np.nan)
+  hr[S:] = 0.0                               # the row's zero pad
+  for iw in range(4):
+    c0 = 4 * iw
+    ee, eo, oa, ob = np.zeros(4), np.zeros(4), np.zeros(4), np.zeros(4)
+    ee16 = o16 = 0.0
+    for j2 in range(16):
+      m0, m1, m2, m3 = m[4 * j2:4 * j2 + 4]
+      ee += m0 * te[2 * j2, c0:c0 + 4]
+      eo += m2 * te[2 * j2 + 1, c0:c0 + 4]
+      oa += m1 * to[2 * j2, 8 * iw:8 * iw + 4] + m3 * to[2 * j2 + 1, 8 * iw:8 * iw + 4]
+      ob += m1 * to[2 * j2, 8 * iw + 4:8 * iw + 8] + m3 * to[2 * j2 + 1, 8 * iw + 4:8 * iw + 8]
+      ee16 += m0 * te[2 * j2, 16]
+      o16 += m1 * to[2 * j2, 32] + m3 * to[2 * j2 + 1, 32]
+    ee += m[64] * te[32, c0:c0 + 4]
+    ee16 += m[64] * te[32, 16]
+    e_a, e_b = ee + eo, ee - eo              # E[n], E[32 - n]
+    vpa = win[shift + c0:shift + c0 + 4] * (e_a + oa)
+    vma = win[c0:c0 + 4] * (e_a - oa)
+    vpb = win[Q + c0:Q + c0 + 4] * (e_b + ob)          # win[64 + (32 - n)] == win[32 + n]
+    vmb = win[shift + Q + c0:shift + Q + c0 + 4] * (e_b - ob)
+
+    def up(base, v):
+      hr[base:base + 4] = v
+
+    def down(base, v, first=True):
+      if first:
+        hr[base] = v[0]
+      hr[base - 3:base] = v[3:0:-1]
+
+    up(shift + c0, vpa); down(shift - c0, vpa)
+    up(c0, vma); down(S - c0, vma, first=(c0 != 0))
+    down(shift + Q - c0, vpb); up(Q + c0, vpb)
+    down(Q - c0, vmb); up(shift + Q + c0, vmb)
+    if iw == 3:
+      hr[shift + 16] = hr[shift - 16] = win[shift + 16] * (ee16 + o16)
+      hr[16] = hr[S - 16] = win[16] * (ee16 - o16)
+  assert not np.isnan(hr[:S]).any()
+  assert np.all(hr[S:] == 0.0)
+  want = o.frequency_impulse_response(m[None, None, :], window_size=0, dtype=np.float64)[0, 0]
+  np.testing.assert_allclose(hr[:S], want, rtol=0, atol=1e-14)
+
+
 def test_overlap_and_add_and_frame():
   x = np.arange(10.0)[None]
   fr = o.frame_pad_end(x, 4, 4)
