@@ -532,6 +532,23 @@ def run_ours(args):
     except Exception as e:  # pylint: disable=broad-except
       extra['c2_error'] = repr(e)
     try:
+      # SURVEY 8(d)'s worst case for the compute bound: f0 = 60 Hz (+-3 % vibrato), so
+      # all 100 harmonics stay below Nyquist in every frame - the same decoder, B=256
+      from tests.util import synth_inputs as _si
+      hw = _si(B, N_FRAMES, N_HARM, N_BANDS, N_SAMPLES, seed=91, f0_lo=60.0, f0_hi=60.0)
+      setsw = []
+      for s in range(2):     # 2 x 236 MB > 2x L2
+        d = {k: torch.from_numpy(hw[k]).to(dev) for k in
+             ('amps', 'harmonic_distribution', 'f0_hz', 'noise_magnitudes')}
+        d['amps'] = d['amps'] + 0.01 * s
+        setsw.append(d)
+      msw = timed(lambda i: group(setsw[i % 2]), 20, 4, collective=False) / 20
+      extra['worst_case_f0_60hz_all_harmonics_live_ms_per_step'] = msw
+      extra['worst_case_samples_per_s'] = B * N_SAMPLES / (msw * 1e-3)
+      del setsw, hw
+    except Exception as e:  # pylint: disable=broad-except
+      extra['worst_case_error'] = repr(e)
+    try:
       # configs[0]: Harmonic only, B=1, 16000 samples, 64 harmonics, 250 frames
       from tests.util import synth_inputs
       c1 = synth_inputs(1, 250, 64, 65, 16000, seed=5)
