@@ -49,6 +49,84 @@ def test_reverb_value_errors_and_masking():
   assert rev._match_dimensions(torch.zeros(3, 10), torch.ones(4)).shape == (3, 4)
 
 
+def test_filtered_noise_reverb_constructor_and_errors():
+  """effects.py:205-238, 266-270."""
+  from ddsp_b200 import effects
+  rev = effects.FilteredNoiseReverb()
+  assert (rev.name, rev.trainable, rev._add_dry, rev._n_frames, rev._n_filter_banks) == (
+      'filtered_noise_reverb', False, True, 1000, 16)
+  syn = rev._synth
+  assert (syn.n_samples, syn.window_size, syn.initial_bias) == (48000, 257, -3.0)
+  assert syn.scale_fn is core.exp_sigmoid
+  with pytest.raises(ValueError, match='Must provide "magnitudes" tensor'):
+    rev.get_controls(np.zeros((2, 100), np.float32))
+  with pytest.raises(ValueError, match='Must provide "ir" tensor'):
+    effects.Reverb().get_controls(np.zeros((2, 100), np.float32))
+
+
+@pytest.mark.parametrize('trainable', [False, True])
+def test_filtered_noise_reverb_composition_matches_reference(monkeypatch, trainable):
+  """The host logic of FilteredNoiseReverb (effects.py:202-278 on top of Reverb's
+  28-117) against the UNMODIFIED reference class run on the NumPy shim, with the
+  same noise and, when trainable, the same learned magnitudes.  The CUDA kernels
+  are replaced by the oracle here (they have their own parity tests): what is under
+  test is the composition - scale + bias, synthesis of the impulse response, tiling
+  of the single learned response, dry-tap masking, 'same' convolution with zero
+  delay compensation, dry mix."""
+  from oracle import ref_on_shim
+  if not ref_on_shim.available():
+    pytest.skip('reference sources not present')
+  from ddsp_b200 import effects
+  ref = ref_on_shim.load()
+  tf = ref_on_shim.tf()
+  rng = np.random.default_rng(5)
+  B, N, L, F, NB, WS = 2, 3000, 1920, 40, 16, 257
+  audio = rng.standard_normal((B, N)).astype(np.float32)
+  mags = rng.standard_normal((1 if trainable else B, F, NB)).astype(np.float32)
+  noise = rng.uniform(-1, 1, (mags.shape[0], L)).astype(np.float32)
+
+  # ---- the reference, on the shim, with its random draw pinned ----
+  monkeypatch.setattr(tf.random, 'uniform',
+                      lambda shape, minval=0, maxval=1, **kw: tf.constant(noise))
+  r = ref.effects.FilteredNoiseReverb(trainable=trainable, reverb_length=L, window_size=WS,
+                                      n_frames=F, n_filter_banks=NB)
+  if trainable:
+    r.build(None)
+    r._magnitudes = tf.constant(mags[0])
+    want = ref_on_shim.to_numpy(r(audio))
+  else:
+    want = ref_on_shim.to_numpy(r(audio, mags))
+
+  # ---- ours, kernels swapped for the oracle ----
+  def t32(x, device=None):
+    return torch.as_tensor(np.asarray(x.detach() if isinstance(x, torch.Tensor) else x,
+                                      dtype=np.float32))
+  monkeypatch.setattr(core, 'torch_float32', t32)
+  monkeypatch.setattr(core, 'noise_controls', lambda m, bias, scale=True: torch.from_numpy(
+      o.noise_get_controls(t32(m).numpy(), initial_bias=bias, scale=scale,
+                           dtype=np.float32)['magnitudes']))
+  monkeypatch.setattr(core, 'filtered_noise', lambda m, n, window_size=257, noise=None, **kw:
+                      torch.from_numpy(o.noise_get_signal(t32(m).numpy(), t32(noise).numpy(),
+                                                          window_size=window_size,
+                                                          dtype=np.float32)))
+  monkeypatch.setattr(core, 'fft_convolve', lambda a, ir, padding='same',
+                      delay_compensation=-1, **kw: torch.from_numpy(
+                          o.fft_convolve(t32(a).numpy(), t32(ir).numpy(), padding=padding,
+                                         delay_compensation=delay_compensation,
+                                         dtype=np.float32)))
+  rev = effects.FilteredNoiseReverb(trainable=trainable, reverb_length=L, window_size=WS,
+                                    n_frames=F, n_filter_banks=NB)
+  rev._synth.injected_noise = torch.from_numpy(noise)
+  with torch.no_grad():
+    if trainable:
+      rev._magnitudes = torch.from_numpy(mags[0]).requires_grad_(True)
+      got = rev(audio).numpy()
+    else:
+      got = rev(audio, mags).numpy()
+  assert got.shape == want.shape == (B, N)
+  assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('taps,add_dry', [(3000, True), (48000, False), (200, True)])
 def test_reverb_matches_oracle(taps, add_dry):
