@@ -743,6 +743,57 @@ def frequency_impulse_response(magnitudes, window_size: int = 0):
   return ir
 
 
+def apply_window_to_impulse_response(impulse_response, window_size: int = 0,
+                                     causal: bool = False):
+  """core.apply_window_to_impulse_response (core.py:1477-1531) for callers of the
+  reference function: zero-phase (or `causal`) impulse responses [..., ir_size] ->
+  Hann-windowed, causal form, cropped to `window_size` (made odd) when that is
+  shorter.  Frame-rate torch ops on whatever device the input lives on; the
+  synthesis path never calls it - `frequency_impulse_response` and the fused noise
+  kernels build the windowed taps straight from the magnitudes."""
+  ir = _as_f32(impulse_response)
+  if causal:
+    ir = torch.fft.fftshift(ir, dim=-1)
+  ir_size = int(ir.shape[-1])
+  if window_size <= 0 or window_size > ir_size:
+    window_size = ir_size
+  # tf.signal.hann_window: periodic for even lengths, symmetric for odd ones
+  window = torch.hann_window(window_size, periodic=(window_size % 2 == 0),
+                             dtype=torch.float32, device=ir.device)
+  padding = ir_size - window_size
+  if padding > 0:
+    half_idx = (window_size + 1) // 2
+    window = torch.cat([window[half_idx:],
+                        torch.zeros(padding, dtype=torch.float32, device=ir.device),
+                        window[:half_idx]], dim=0)
+  else:
+    window = torch.fft.fftshift(window, dim=-1)
+  ir = window * ir
+  if padding > 0:
+    first_half_start = (ir_size - (half_idx - 1)) + 1
+    second_half_end = half_idx + 1
+    ir = torch.cat([ir[..., first_half_start:], ir[..., :second_half_end]], dim=-1)
+  else:
+    ir = torch.fft.fftshift(ir, dim=-1)
+  return ir
+
+
+def crop_and_compensate_delay(audio, audio_size: int, ir_size: int, padding: Text,
+                              delay_compensation: int):
+  """core.crop_and_compensate_delay (core.py:1338-1379): the slice
+  `audio[:, start:-end]` of a convolution output, with the reference's ValueError and
+  its Python slice semantics (an `end` of 0 gives an empty result).  A view - no
+  kernel; `fft_convolve` applies the same index arithmetic (`_crop_range`) inside its
+  kernels instead of materialising the uncropped signal."""
+  if not isinstance(audio, torch.Tensor):
+    audio = torch.as_tensor(np.asarray(audio, dtype=np.float32))
+  start, _, _ = _crop_range(int(audio.shape[-1]), audio_size, ir_size, padding,
+                            delay_compensation)
+  crop_size = ir_size + audio_size - 1 if padding == 'valid' else audio_size
+  end = (int(audio.shape[-1]) - crop_size) - start
+  return audio[:, start:-end]
+
+
 def _crop_range(total_size, audio_size, ir_size, padding, delay_compensation):
   """Index arithmetic of crop_and_compensate_delay (core.py:1338-1379),
   including Python's slice semantics of `audio[:, start:-end]`."""

@@ -50,10 +50,16 @@ __device__ __forceinline__ void ir_tap(const IrGeom& g, int j, int* idx_out,
   if (idx < 0) idx += g.S0;
   float w;
   if (g.padded) {
-    if (idx < g.ws - g.half) {
-      w = 0.5f - 0.5f * cospif(2.0f * (float)(g.half + idx) / (float)g.ws);
+    // tf.signal.hann_window(ws): 0.5 - 0.5 cos(2 pi k / d) with d = ws for even ws and
+    // d = ws - 1 for odd ws (window_ops._raised_cosine_window: an odd length gives the
+    // symmetric window whatever `periodic` says); a window of one sample is 1.
+    const float d = (float)((g.ws & 1) ? g.ws - 1 : g.ws);
+    if (g.ws == 1) {
+      w = (idx >= g.S0 - g.half) ? 1.0f : 0.f;
+    } else if (idx < g.ws - g.half) {
+      w = 0.5f - 0.5f * cospif(2.0f * (float)(g.half + idx) / d);
     } else if (idx >= g.S0 - g.half) {
-      w = 0.5f - 0.5f * cospif(2.0f * (float)(idx - (g.S0 - g.half)) / (float)g.ws);
+      w = 0.5f - 0.5f * cospif(2.0f * (float)(idx - (g.S0 - g.half)) / d);
     } else {
       w = 0.f;
     }

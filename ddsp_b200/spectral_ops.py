@@ -32,8 +32,7 @@ def stft(audio, frame_size=2048, overlap=0.75, pad_end=True):
   else:
     n_frames = max(0, 1 + (n - frame_size) // step)
   frames = audio.unfold(-1, frame_size, step)[..., :n_frames, :]
-  window = torch.hann_window(frame_size, periodic=True, dtype=torch.float32,
-                             device=audio.device)
+  window = _hann(frame_size, audio.device)
   return torch.fft.rfft(frames * window, n=fft_length, dim=-1)
 
 
@@ -49,7 +48,9 @@ _WINDOWS = {}
 def _hann(frame_size, device):
   key = (int(frame_size), str(device))
   if key not in _WINDOWS:
-    _WINDOWS[key] = torch.hann_window(int(frame_size), periodic=True,
+    # tf.signal.hann_window: periodic for even lengths, symmetric for odd ones
+    _WINDOWS[key] = torch.hann_window(int(frame_size),
+                                      periodic=(int(frame_size) % 2 == 0),
                                       dtype=torch.float32, device=device)
   return _WINDOWS[key]
 

@@ -83,11 +83,17 @@ def exp_sigmoid(x, exponent=10.0, max_value=2.0, threshold=1e-7,
 # TF op restatements
 # ----------------------------------------------------------------------------
 def hann_window(n, dtype=np.float64):
-  """tf.signal.hann_window(n) (periodic=True): 0.5 - 0.5 cos(2 pi k / n)."""
+  """tf.signal.hann_window(n) (periodic=True): 0.5 - 0.5 cos(2 pi k / d) with d = n
+  for even n and d = n - 1 for odd n - TensorFlow's `_raised_cosine_window`
+  (window_ops.py: `n = window_length + periodic * even - 1`) gives the SYMMETRIC
+  window whenever the length is odd, `periodic` or not.  (Until the last session of
+  round 2 this function used d = n throughout; the unmodified reference on the shim
+  exposed it on odd filter windows, e.g. window_size=257 with more than 129 bins.)"""
   if n == 1:
     return np.ones([1], dtype)
   k = np.arange(n, dtype=np.float64)
-  return (0.5 - 0.5 * np.cos(TWO_PI * k / n)).astype(dtype)
+  d = n if n % 2 == 0 else n - 1
+  return (0.5 - 0.5 * np.cos(TWO_PI * k / d)).astype(dtype)
 
 
 def overlap_and_add(frames, hop):

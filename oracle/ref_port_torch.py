@@ -18,6 +18,12 @@ import torch
 F32 = torch.float32
 
 
+def _tf_hann(n):
+  """tf.signal.hann_window(n): periodic for even n, symmetric for odd n
+  (window_ops._raised_cosine_window's `even` term)."""
+  return torch.hann_window(n, periodic=(n % 2 == 0), dtype=F32)
+
+
 def exp_sigmoid(x):
   """core.py:386-404."""
   return 2.0 * torch.sigmoid(x)**math.log(10.0) + 1e-7
@@ -41,7 +47,7 @@ def _upsample_with_windows(x, n_out):
   x = torch.cat([x, x[:, -1:, :]], dim=1)
   n_frames = x.shape[1]
   hop = n_out // (n_frames - 1)
-  window = torch.hann_window(2 * hop, periodic=True, dtype=F32)
+  window = _tf_hann(2 * hop)
   x = x.permute(0, 2, 1)                                  # [B, C, frames]
   xw = x[:, :, :, None] * window[None, None, None, :]     # [B, C, frames, 2hop]
   b, c, f, w = xw.shape
@@ -92,7 +98,7 @@ def noise_signal(mags, n_samples, window_size=0, noise=None):
   ir = torch.fft.irfft(torch.complex(mags, torch.zeros_like(mags)))
   ir_size = ir.shape[-1]
   ws = window_size if 0 < window_size <= ir_size else ir_size
-  window = torch.hann_window(ws, periodic=True, dtype=F32)
+  window = _tf_hann(ws)
   padding = ir_size - ws
   if padding > 0:
     half = (ws + 1) // 2
@@ -140,7 +146,7 @@ def spectral_loss(target, audio, fft_sizes=(2048, 1024, 512, 256, 128, 64),
     step = size // 4
     n_frames = -(-n // step)
     pad = (n_frames - 1) * step + size - n
-    win = torch.hann_window(size, periodic=True, dtype=F32)
+    win = _tf_hann(size)
 
     def mag(x):
       fr = torch.nn.functional.pad(x, (0, pad)).unfold(-1, size, step)

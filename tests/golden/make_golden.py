@@ -216,9 +216,37 @@ def spectral_loss():
   return out
 
 
+IR_CASES = [(65, 0), (65, 257), (65, 63), (65, 64), (100, 51), (100, 50), (513, 257),
+            (513, 22), (1025, 257), (16, 257), (65, 3)]
+
+
+def impulse_responses():
+  """core.frequency_impulse_response (core.py:1534-1565) and frequency_filter
+  (1628-1655) for even AND odd window sizes: tf.signal.hann_window is periodic
+  for even lengths and symmetric for odd ones (window_ops._raised_cosine_window),
+  which a restatement gets wrong unless it is checked on an odd window shorter than
+  the impulse response (window_size=257 with more than 129 bins, e.g.)."""
+  ddsp = ref_on_shim.load()
+  rng = np.random.default_rng(808)
+  out = {}
+  for nb, ws in IR_CASES:
+    m = rng.uniform(0.0, 1.0, (2, 3, nb)).astype(np.float32)
+    n, w = _both(lambda: ddsp.core.frequency_impulse_response(m, ws))
+    out['mags_%d_%d' % (nb, ws)] = m
+    out['ir_f32_%d_%d' % (nb, ws)] = n
+    out['ir_wide_%d_%d' % (nb, ws)] = w.astype(np.float64)
+  noise = rng.uniform(-1.0, 1.0, (2, 960)).astype(np.float32)
+  mags = rng.uniform(0.0, 1.0, (2, 20, 513)).astype(np.float32)
+  n, w = _both(lambda: ddsp.core.frequency_filter(noise, mags, window_size=257))
+  out.update(filter_noise=noise, filter_mags=mags, filter_f32=n,
+             filter_wide=w.astype(np.float64))
+  return out
+
+
 FIXTURES = dict(c1_harmonic=c1_harmonic, decoder_small=decoder_small, c2_item=c2_item,
                 harmonic_shifts=harmonic_shifts, resample_methods=resample_methods,
-                angular_cumsum=angular_cumsum, spectral_loss=spectral_loss)
+                angular_cumsum=angular_cumsum, spectral_loss=spectral_loss,
+                impulse_responses=impulse_responses)
 
 
 def compare(name, got, want, atol=0.0):

@@ -177,3 +177,24 @@ def test_oracle_matches_reference_spectral_loss():
     got = o.spectral_loss(g['target'], g['audio'], **kw)
     assert abs(got - float(g['loss_wide_' + tag])) <= 1e-9 * abs(got)
     assert abs(got - float(g['loss_f32_' + tag])) <= 2e-5 * abs(got)
+
+
+def test_oracle_matches_reference_impulse_responses_odd_and_even_windows():
+  """The windowed impulse responses of the reference for even and ODD window sizes
+  (tf.signal.hann_window: periodic for even lengths, symmetric for odd ones) and one
+  filtered-noise signal through an odd window shorter than the response."""
+  from tests.golden.make_golden import IR_CASES
+  g = gold('impulse_responses')
+  for nb, ws in IR_CASES:
+    m = g['mags_%d_%d' % (nb, ws)]
+    want32, want64 = g['ir_f32_%d_%d' % (nb, ws)], g['ir_wide_%d_%d' % (nb, ws)]
+    got32 = o.frequency_impulse_response(m, ws, dtype=np.float32)
+    got64 = o.frequency_impulse_response(m.astype(np.float64), ws, dtype=np.float64)
+    assert got32.shape == want32.shape == got64.shape, (nb, ws, got32.shape, want32.shape)
+    assert np.abs(got32 - want32).max() <= 1e-6, (nb, ws)
+    assert np.abs(got64 - want64).max() <= 1e-12, (nb, ws)
+  got = o.frequency_filter(g['filter_noise'].astype(np.float64),
+                           g['filter_mags'].astype(np.float64), window_size=257)
+  emax, el2 = rel_err(got, g['filter_wide'])
+  assert emax <= 1e-9 and el2 <= 1e-9
+
