@@ -969,7 +969,10 @@ def _cubic_table():
   """resize_bicubic_op.cc InitCoeffsTable(a = -0.75), the legacy (non
   half-pixel) Keys kernel sampled at 1025 offsets, float32 entries."""
   a = -0.75
-  tab = np.empty(((_K_TABLE + 1) * 2,), _F32().type)
+  # float32 in BOTH modes: the table is a constant of TensorFlow's kernel (`static
+  # const float*`), not one of the reference's float32 tensors - and it is built once
+  # per process, so its precision must not depend on which mode asked for it first
+  tab = np.empty(((_K_TABLE + 1) * 2,), np.float32)
   for i in builtins.range(_K_TABLE + 1):
     x = i * 1.0 / _K_TABLE
     tab[2 * i] = ((a + 2) * x - (a + 3)) * x * x + 1
